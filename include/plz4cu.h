@@ -1,0 +1,175 @@
+/*
+ * plz4cu.h — C ABI of the B200-native LZ4 block engine behind plz4's independent-block path.
+ *
+ * This is the drop-in boundary: what a cgo shim replacing plz4's internal/pkg/clz4/clz4.go
+ * (and the per-block fan-out in internal/pkg/async) binds to.  Plain pointers and sizes only.
+ * Reference interface each entry point replaces is cited as file:line relative to the plz4 tree.
+ *
+ * Block record layout (identical to blk.CompressToBlk, internal/pkg/blk/blk.go:87-106):
+ *     [ LE32 size | bit31 = stored uncompressed ][ payload ][ LE32 xxh32(payload) if block checksum ]
+ *
+ * Error convention
+ *   - Infrastructure failures (CUDA error, bad argument) : functions return a negative
+ *     PLZ4CU_ERR_* code; plz4cu_last_error() has the text.  A shim must map these onto a
+ *     non-ErrCompress error so the stream aborts (blk/blk.go:82-85) instead of storing raw.
+ *   - Per-block codec results are reported per block, never as a call failure:
+ *       compress   : rec_len[b] is the record length; an incompressible block is stored raw
+ *                    with bit 31 set, exactly what blk.go:78-92 does on ErrCompress.
+ *       decompress : out_len[b] >= 0 is the decoded size; < 0 is
+ *                      -(byte offset)-1        the LZ4_decompress_safe code (clz4.go:47-60, lz4.c:2443)
+ *                      PLZ4CU_E_BLOCKHASH      xxh32 mismatch          (blk/frame.go:114-127)
+ *                      PLZ4CU_E_OVERFLOW       size word > block size  (blk/frame.go:79-81)
+ */
+#ifndef PLZ4CU_H
+#define PLZ4CU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PLZ4CU_API __attribute__((visibility("default")))
+#else
+#define PLZ4CU_API
+#endif
+
+#define PLZ4CU_OK                 0
+#define PLZ4CU_ERR_CUDA          -1   /* a CUDA runtime call failed                              */
+#define PLZ4CU_ERR_ARG           -2   /* invalid argument                                        */
+#define PLZ4CU_ERR_NOMEM         -3   /* allocation failed                                       */
+#define PLZ4CU_ERR_NODEVICE      -4   /* no usable GPU: the engine never falls back to the CPU   */
+
+#define PLZ4CU_E_BLOCKHASH   ((int32_t)-0x7F000001)
+#define PLZ4CU_E_OVERFLOW    ((int32_t)-0x7F000002)
+
+#define PLZ4CU_STORED_BIT    0x80000000u
+#define PLZ4CU_REC_OVERHEAD  8u          /* size word + checksum, blk/pool.go:15 szOverhead */
+#define PLZ4CU_DICT_MAX      65536u      /* compress/dict.go:3 lz4DictSz */
+
+typedef struct plz4cu_dict plz4cu_dict_t;
+typedef void* plz4cu_stream_t;           /* a cudaStream_t; NULL = the legacy default stream */
+
+/* ---------------------------------------------------------------- lifecycle */
+
+/* Number of visible CUDA devices, or PLZ4CU_ERR_NODEVICE. */
+PLZ4CU_API int plz4cu_device_count(void);
+/* Bind the calling thread to `device` and warm the context.  0 or a negative PLZ4CU_ERR_*. */
+PLZ4CU_API int plz4cu_init(int device);
+/* Text of the last failure on this thread ("" if none). */
+PLZ4CU_API const char* plz4cu_last_error(void);
+/* "plz4cu <version> sm_100a" */
+PLZ4CU_API const char* plz4cu_version(void);
+/* Kernels launched by this process so far (bench.py's gpu_launches). */
+PLZ4CU_API uint64_t plz4cu_launch_count(void);
+
+/* ---------------------------------------------------------------- sizes */
+
+/* compress.CompressBound (compress/compress.go:83-85) == LZ4_COMPRESSBOUND (clz4/lz4.h:215). */
+PLZ4CU_API size_t plz4cu_compress_bound(size_t n);
+
+/* ---------------------------------------------------------------- memory */
+
+/* Pinned host slabs: what blk.BorrowBlk/ReturnBlk (blk/pool.go:35-69) hand out in the GPU build. */
+PLZ4CU_API void* plz4cu_host_alloc(size_t n);
+PLZ4CU_API void plz4cu_host_free(void* p);
+/* Outstanding pinned slabs — the blk.CntBorrowed() leak gauge (blk/pool.go:29-33). */
+PLZ4CU_API int64_t plz4cu_host_outstanding(void);
+PLZ4CU_API void* plz4cu_device_alloc(size_t n);
+PLZ4CU_API void plz4cu_device_free(void* p);
+
+/* ---------------------------------------------------------------- dictionary */
+
+/* clz4.NewDictCtx (clz4/clz4.go:101-120) + compress.NewDictT (compress/dict.go:10-16,43-56):
+ * keeps the last 64 KiB of `d` on the device and builds the match table once.  Host pointer. */
+PLZ4CU_API plz4cu_dict_t* plz4cu_dict_create(const void* d, size_t n);
+PLZ4CU_API void plz4cu_dict_destroy(plz4cu_dict_t* dict);
+
+/* ---------------------------------------------------------------- device-resident batches
+ * All pointers below are DEVICE pointers.  Calls are asynchronous on `stream`.
+ *
+ * Replaces the body of async/writer.go:232-282 compressLoop -> blk.CompressToBlk (blk/blk.go:69-109)
+ * -> Compressor.Compress (compress/indie.go:66-74, :27-35) for a whole batch of independent blocks.
+ *   src_base + src_off[b], src_len[b]   : block b's bytes (src_len[b] <= dst_cap... see below)
+ *   dst_cap                             : room given to the compressor (bsz on the frame path, blk.go:73;
+ *                                         CompressBound on the raw path, plz4_block.go:105-107)
+ *   rec_base + b*rec_stride             : slot receiving block b's record; rec_stride >= max(dst_cap,
+ *                                         max src_len) + 8 and a multiple of 16
+ *   rec_len[b]                          : record length written (4 + n [+ 4])
+ *   raw_blocks != 0                     : raw block API (plz4_block.go:96-119): no size word, no checksum,
+ *                                         the slot holds just the LZ4 block and rec_len[b] is its size,
+ *                                         or 0 when it does not fit dst_cap (clz4.go:40-42 ErrLz4Compress)
+ */
+PLZ4CU_API int plz4cu_compress_batch_device(plz4cu_stream_t stream,
+                                 const void* src_base, const uint64_t* src_off, const uint32_t* src_len,
+                                 uint32_t nblk, uint32_t dst_cap, int block_checksum, int raw_blocks,
+                                 const plz4cu_dict_t* dict,
+                                 void* rec_base, uint32_t rec_stride, uint32_t* rec_len);
+
+/* Replaces async/reader.go:192-221 _decompressLoop -> BlkT.Decompress (blk/blk.go:50-61) ->
+ * Decompressor.Decompress (compress/decompress.go:32-38, :46-58), plus the block-hash check and
+ * size-overflow check of blk/frame.go:79-81,114-127, for a whole batch.
+ *   rec_base + rec_off[b]               : block b's record ([size][payload][xxh]) when raw_blocks == 0,
+ *                                         or its bare LZ4 block of raw_len[b] bytes when raw_blocks != 0
+ *   raw_len                             : only read when raw_blocks != 0
+ *   dst_base + b*dst_stride, dst_cap    : output slot and capacity (bsz on the frame path, blk.go:51)
+ *   out_len[b]                          : see "Error convention" above
+ */
+PLZ4CU_API int plz4cu_decompress_batch_device(plz4cu_stream_t stream,
+                                   const void* rec_base, const uint64_t* rec_off, const uint32_t* raw_len,
+                                   uint32_t nblk, uint32_t dst_cap, int verify_checksum, int raw_blocks,
+                                   const plz4cu_dict_t* dict,
+                                   void* dst_base, uint64_t dst_stride, int32_t* out_len);
+
+/* Pack fixed-stride record slots into one contiguous run in block order (what writeLoop's in-order
+ * wr.Write does, async/writer.go:316-348).  packed_off[b] receives each record's start (the dstMark
+ * a progress callback reports, async/writer.go:329); packed_off[nblk] the total.  Device pointers. */
+PLZ4CU_API int plz4cu_pack_records_device(plz4cu_stream_t stream,
+                               const void* rec_base, uint32_t rec_stride, const uint32_t* rec_len,
+                               uint32_t nblk, void* packed, uint64_t* packed_off);
+
+/* Synthetic benchmark input (SURVEY.md §8d logtext): fills n bytes of stream `seed` starting at
+ * 64 KiB segment `first_seg`.  Device pointer / host pointer flavours produce identical bytes. */
+PLZ4CU_API int plz4cu_gen_logtext_device(plz4cu_stream_t stream, uint32_t seed, uint64_t first_seg, void* dst, uint64_t n);
+PLZ4CU_API int plz4cu_gen_logtext_host(uint32_t seed, uint64_t first_seg, void* dst, uint64_t n);
+
+/* ---------------------------------------------------------------- host-resident batches
+ * Same contracts with HOST pointers (pinned for full speed): the engine stages H2D, runs the
+ * kernels and copies results back, pipelined over internal streams.  Synchronous.
+ * compress : records are returned PACKED in block order in `packed` (capacity packed_cap bytes,
+ *            worst case nblk*(max_len+8)); packed_off has nblk+1 entries.
+ */
+PLZ4CU_API int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const uint32_t* src_len,
+                               uint32_t nblk, uint32_t dst_cap, int block_checksum, int raw_blocks,
+                               const plz4cu_dict_t* dict,
+                               void* packed, uint64_t packed_cap, uint64_t* packed_off);
+PLZ4CU_API int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const uint64_t* rec_off, const uint32_t* raw_len,
+                                 uint32_t nblk, uint32_t dst_cap, int verify_checksum, int raw_blocks,
+                                 const plz4cu_dict_t* dict,
+                                 void* dst, uint64_t dst_stride, int32_t* out_len);
+
+/* ---------------------------------------------------------------- per-block shims
+ * Exact int-return semantics of the C symbols clz4.go binds, so the existing one-block-at-a-time
+ * Compressor / Decompressor implementations keep working (batch of one; host pointers):
+ *   plz4cu_compress_fast          LZ4_compress_fast(src,dst,n,cap,1)              clz4.go:31-45
+ *   plz4cu_compress_fast_dict     resetStream_fast+attach_dictionary+fast_continue clz4.go:160-179
+ *   plz4cu_decompress_safe        LZ4_decompress_safe                             clz4.go:47-60
+ *   plz4cu_decompress_safe_dict   LZ4_decompress_safe_usingDict                   clz4.go:62-78
+ * Return: compress 0 = does not fit; decompress < 0 = corrupt input.  Infrastructure failures
+ * return INT32_MIN (check plz4cu_last_error()).
+ */
+PLZ4CU_API int plz4cu_compress_fast(const void* src, int n, void* dst, int cap);
+PLZ4CU_API int plz4cu_compress_fast_dict(const plz4cu_dict_t* dict, const void* src, int n, void* dst, int cap);
+PLZ4CU_API int plz4cu_decompress_safe(const void* src, int n, void* dst, int cap);
+PLZ4CU_API int plz4cu_decompress_safe_dict(const plz4cu_dict_t* dict, const void* src, int n, void* dst, int cap);
+
+/* xxh32.ChecksumZero (xxh32/xxh32zero.go:238-280) of nblk device buffers, one warp each. */
+PLZ4CU_API int plz4cu_xxh32_batch_device(plz4cu_stream_t stream, const void* base, const uint64_t* off,
+                              const uint32_t* len, uint32_t nblk, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLZ4CU_H */

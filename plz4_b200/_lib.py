@@ -1,0 +1,87 @@
+"""ctypes binding of libplz4cu.so (include/plz4cu.h).
+
+This module is plumbing: it declares the C ABI to ctypes and nothing else.  There is no CPU
+codec behind it — if the shared library is missing it is built, and if it cannot be built or
+loaded the import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(_HERE, "..", "include", "plz4cu.h")
+
+ERR_CUDA, ERR_ARG, ERR_NOMEM, ERR_NODEVICE = -1, -2, -3, -4
+E_BLOCKHASH = -0x7F000001
+E_OVERFLOW = -0x7F000002
+STORED_BIT = 0x80000000
+INT32_MIN = -(1 << 31)
+
+_vp, _u32, _u64, _i32, _int, _sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_int, C.c_size_t
+
+# name -> (restype, argtypes); must list every PLZ4CU_API symbol of the header (tests check this)
+SIGNATURES = {
+    "plz4cu_device_count": (_int, []),
+    "plz4cu_init": (_int, [_int]),
+    "plz4cu_last_error": (C.c_char_p, []),
+    "plz4cu_version": (C.c_char_p, []),
+    "plz4cu_launch_count": (_u64, []),
+    "plz4cu_compress_bound": (_sz, [_sz]),
+    "plz4cu_host_alloc": (_vp, [_sz]),
+    "plz4cu_host_free": (None, [_vp]),
+    "plz4cu_host_outstanding": (C.c_int64, []),
+    "plz4cu_device_alloc": (_vp, [_sz]),
+    "plz4cu_device_free": (None, [_vp]),
+    "plz4cu_dict_create": (_vp, [_vp, _sz]),
+    "plz4cu_dict_destroy": (None, [_vp]),
+    "plz4cu_compress_batch_device": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _int, _int, _vp, _vp, _u32, _vp]),
+    "plz4cu_decompress_batch_device": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _int, _int, _vp, _vp, _u64, _vp]),
+    "plz4cu_pack_records_device": (_int, [_vp, _vp, _u32, _vp, _u32, _vp, _vp]),
+    "plz4cu_gen_logtext_device": (_int, [_vp, _u32, _u64, _vp, _u64]),
+    "plz4cu_gen_logtext_host": (_int, [_u32, _u64, _vp, _u64]),
+    "plz4cu_compress_batch_host": (_int, [_vp, _vp, _vp, _u32, _u32, _int, _int, _vp, _vp, _u64, _vp]),
+    "plz4cu_decompress_batch_host": (_int, [_vp, _u64, _vp, _vp, _u32, _u32, _int, _int, _vp, _vp, _u64, _vp]),
+    "plz4cu_compress_fast": (_int, [_vp, _int, _vp, _int]),
+    "plz4cu_compress_fast_dict": (_int, [_vp, _vp, _int, _vp, _int]),
+    "plz4cu_decompress_safe": (_int, [_vp, _int, _vp, _int]),
+    "plz4cu_decompress_safe_dict": (_int, [_vp, _vp, _int, _vp, _int]),
+    "plz4cu_xxh32_batch_device": (_int, [_vp, _vp, _vp, _vp, _u32, _vp]),
+}
+
+
+def header_symbols() -> list[str]:
+    """Every function the public header declares."""
+    with open(HEADER) as f:
+        return sorted(set(re.findall(r"PLZ4CU_API[^;(]*?\b(plz4cu_\w+)\s*\(", f.read())))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (building if stale) libplz4cu.so and declare every signature."""
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)            # AttributeError here == header/library mismatch: loud
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class Plz4cuError(RuntimeError):
+    """Infrastructure failure inside the engine (CUDA error, bad argument, no device)."""
+
+
+def check(rc: int, what: str = "") -> int:
+    if rc < 0:
+        msg = lib().plz4cu_last_error().decode(errors="replace")
+        raise Plz4cuError(f"{what or 'plz4cu'} failed ({rc}): {msg}")
+    return rc

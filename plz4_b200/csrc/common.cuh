@@ -1,0 +1,161 @@
+// common.cuh — device helpers shared by the sm_100a kernels (warp-level byte plumbing + xxh32).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FULL_MASK 0xffffffffu
+
+namespace plz4 {
+
+constexpr int MINMATCH = 4;
+constexpr int LASTLITERALS = 5;
+constexpr int MFLIMIT = 12;
+constexpr uint32_t MAX_DISTANCE = 65535;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ---------------------------------------------------------------- unaligned access
+
+// 4 bytes at an arbitrary byte address, read as two aligned words + funnel shift.  The aligned
+// words may start up to 3 bytes before p / end up to 3 bytes after p+4; callers guarantee those
+// bytes lie inside the same allocation (true for any interior pointer of a CUDA allocation).
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p)
+{
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t lo = w[0];
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, w[1], sh);
+}
+
+__device__ __forceinline__ uint32_t load_u16le(const uint8_t* p)
+{
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+}
+
+// ---------------------------------------------------------------- warp copies
+
+// Forward, non-overlapping copy of n bytes by one warp.  Handles any alignment; moves 16 bytes per
+// lane per step once dst is 16-byte aligned and src happens to share the alignment, 4 bytes per lane
+// when only word alignment can be shared (src re-aligned with a funnel shift), bytes otherwise.
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane)
+{
+    if (n < 64) {
+        for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
+        return;
+    }
+    // head: bring dst to 16-byte alignment
+    uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+    uint32_t nvec = n >> 4;
+    if (mis == 0) {
+        const uint4* s = reinterpret_cast<const uint4*>(src);
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        uint32_t k = lane;
+        for (; k + 96 < nvec; k += 128) {      // 4 loads in flight per lane
+            uint4 a = s[k], b = s[k + 32], c = s[k + 64], e = s[k + 96];
+            d[k] = a; d[k + 32] = b; d[k + 64] = c; d[k + 96] = e;
+        }
+        for (; k < nvec; k += 32) d[k] = s[k];
+    } else if ((mis & 3) == 0) {
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        for (uint32_t k = lane; k < nvec; k += 32) {
+            uint4 v;
+            v.x = s[4 * k]; v.y = s[4 * k + 1]; v.z = s[4 * k + 2]; v.w = s[4 * k + 3];
+            d[k] = v;
+        }
+    } else {
+        // src is byte-misaligned relative to dst: aligned word loads + funnel shift, 16-byte stores
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(src - (mis & 3));
+        uint32_t sh = (mis & 3) * 8;
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        for (uint32_t k = lane; k < nvec; k += 32) {
+            uint32_t w0 = s[4 * k], w1 = s[4 * k + 1], w2 = s[4 * k + 2], w3 = s[4 * k + 3], w4 = s[4 * k + 4];
+            uint4 v;
+            v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+            v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+            d[k] = v;
+        }
+    }
+    uint32_t done = nvec << 4;
+    for (uint32_t k = done + lane; k < n; k += 32) dst[k] = src[k];
+}
+
+// ---------------------------------------------------------------- xxh32 (seed 0)
+
+constexpr uint32_t XP1 = 2654435761u, XP2 = 2246822519u, XP3 = 3266489917u, XP4 = 668265263u,
+                   XP5 = 374761393u;
+
+__device__ __forceinline__ uint32_t rol32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+
+// xxh32.ChecksumZero (xxh32/xxh32zero.go:238-280) of p[0..n) computed by one warp; every lane
+// returns the digest.  The four accumulator chains are inherently serial along the stripes, so
+// lanes 0..3 carry them; the other lanes only help to fetch: a chunk of 32 stripes (512 B) is
+// loaded coalesced (4 words per lane) and handed to the chain lanes with shuffles.
+__device__ __forceinline__ uint32_t warp_xxh32(const uint8_t* p, uint32_t n, int lane)
+{
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t nstripes = n >> 4;
+    const uint32_t nwords = nstripes << 2;
+    uint32_t acc;
+    {
+        int j = lane & 3;
+        acc = (j == 0) ? (XP1 + XP2) : (j == 1) ? XP2 : (j == 2) ? 0u : (0u - XP1);
+    }
+    for (uint32_t base = 0; base < nstripes; base += 32) {
+        uint32_t w[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            uint32_t idx = base * 4 + r * 32 + lane;
+            uint32_t v = 0;
+            if (idx < nwords) {
+                v = wp[idx];
+                if (sh) v = __funnelshift_r(v, wp[idx + 1], sh);
+            }
+            w[r] = v;
+        }
+        uint32_t left = nstripes - base;      // stripes in this chunk (warp-uniform)
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                uint32_t x = __shfl_sync(FULL_MASK, w[r], 4 * t + (lane & 3));
+                if ((uint32_t)(r * 8 + t) < left) acc = rol32(acc + x * XP2, 13) * XP1;
+            }
+        }
+    }
+    uint32_t h;
+    if (n >= 16) {
+        uint32_t v0 = __shfl_sync(FULL_MASK, acc, 0), v1 = __shfl_sync(FULL_MASK, acc, 1);
+        uint32_t v2 = __shfl_sync(FULL_MASK, acc, 2), v3 = __shfl_sync(FULL_MASK, acc, 3);
+        h = rol32(v0, 1) + rol32(v1, 7) + rol32(v2, 12) + rol32(v3, 18);
+    } else {
+        h = XP5;
+    }
+    h += n;
+    uint32_t i = nstripes << 4;
+    for (; i + 4 <= n; i += 4) {
+        uint32_t v = (uint32_t)p[i] | ((uint32_t)p[i + 1] << 8) | ((uint32_t)p[i + 2] << 16) | ((uint32_t)p[i + 3] << 24);
+        h = rol32(h + v * XP3, 17) * XP4;
+    }
+    for (; i < n; i++) h = rol32(h + (uint32_t)p[i] * XP5, 11) * XP1;
+    h ^= h >> 15; h *= XP2; h ^= h >> 13; h *= XP3; h ^= h >> 16;
+    return h;
+}
+
+__device__ __forceinline__ void store_le32(uint8_t* p, uint32_t v)
+{
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+__device__ __forceinline__ uint32_t load_le32(const uint8_t* p)
+{
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+}  // namespace plz4

@@ -1,0 +1,549 @@
+// engine.cu — the C ABI declared in include/plz4cu.h.
+//
+// Device-resident entry points are thin launches on the caller's stream.  Host-resident entry
+// points stage through a per-device pipeline context (grow-only device scratch, two lanes of
+// stream + buffers) so that H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 overlap.
+// There is NO CPU codec in this library: without a usable GPU every entry point fails loudly.
+#include "../../include/plz4cu.h"
+#include "kernels.h"
+#include "logtext.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace plz4;
+
+static_assert(PLZ4CU_E_BLOCKHASH == PLZ4CU_E_BLOCKHASH_, "header/kernels mismatch");
+static_assert(PLZ4CU_E_OVERFLOW == PLZ4CU_E_OVERFLOW_, "header/kernels mismatch");
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int64_t> g_host_outstanding{0};
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                       \
+    do {                                                               \
+        cudaError_t e__ = (call);                                      \
+        if (e__ != cudaSuccess) return fail(PLZ4CU_ERR_CUDA, #call, e__); \
+    } while (0)
+
+int ensure_configured()
+{
+    // per-device function attributes must be set on every device we run on
+    static std::mutex mu;
+    static std::vector<int> done;
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(PLZ4CU_ERR_NODEVICE, "no CUDA device (the engine has no CPU fallback)", e);
+    std::lock_guard<std::mutex> lk(mu);
+    if (std::find(done.begin(), done.end(), dev) != done.end()) return 0;
+    e = configure_compress();
+    if (e != cudaSuccess) return fail(PLZ4CU_ERR_CUDA, "configure_compress", e);
+    done.push_back(dev);
+    return 0;
+}
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)1 << 20);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// one pipeline lane: a stream plus its private scratch
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf in, out, packed, off, len, res, poff;
+    HostBuf h_meta;      // pinned staging for small metadata
+};
+
+struct Pipe {
+    std::mutex mu;
+    int device = -1;
+    Lane lane[2];
+    bool ready = false;
+    int init()
+    {
+        if (ready) return 0;
+        for (auto& l : lane) {
+            CU(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        }
+        ready = true;
+        return 0;
+    }
+};
+
+std::mutex g_pipes_mu;
+std::vector<Pipe*> g_pipes;
+Pipe* pipe_for_current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pipes_mu);
+    if ((int)g_pipes.size() <= dev) g_pipes.resize(dev + 1, nullptr);
+    if (!g_pipes[dev]) { g_pipes[dev] = new Pipe(); g_pipes[dev]->device = dev; }
+    return g_pipes[dev];
+}
+
+inline uint32_t round_up16(uint32_t v) { return (v + 15u) & ~15u; }
+
+}  // namespace
+
+struct plz4cu_dict {
+    uint8_t* d_bytes = nullptr;     // device copy of the last <= 64 KiB
+    uint32_t size = 0;
+    std::vector<uint8_t> h_bytes;
+};
+
+extern "C" {
+
+int plz4cu_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return fail(PLZ4CU_ERR_NODEVICE, "no CUDA device (the engine has no CPU fallback)", e);
+    return n;
+}
+
+int plz4cu_init(int device)
+{
+    int n = plz4cu_device_count();
+    if (n < 0) return n;
+    if (device < 0 || device >= n) return fail(PLZ4CU_ERR_ARG, "plz4cu_init: device out of range");
+    CU(cudaSetDevice(device));
+    CU(cudaFree(0));
+    return ensure_configured();
+}
+
+const char* plz4cu_last_error(void) { return g_err.c_str(); }
+const char* plz4cu_version(void) { return "plz4cu 0.1 sm_100a"; }
+uint64_t plz4cu_launch_count(void) { return g_launches.load(); }
+
+size_t plz4cu_compress_bound(size_t n)
+{
+    if (n > 0x7E000000u) return 0;
+    return n + n / 255 + 16;
+}
+
+void* plz4cu_host_alloc(size_t n)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { fail(PLZ4CU_ERR_NOMEM, "cudaHostAlloc", e); return nullptr; }
+    g_host_outstanding++;
+    return p;
+}
+void plz4cu_host_free(void* p)
+{
+    if (!p) return;
+    cudaFreeHost(p);
+    g_host_outstanding--;
+}
+int64_t plz4cu_host_outstanding(void) { return g_host_outstanding.load(); }
+
+void* plz4cu_device_alloc(size_t n)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n ? n : 1);
+    if (e != cudaSuccess) { fail(PLZ4CU_ERR_NOMEM, "cudaMalloc", e); return nullptr; }
+    return p;
+}
+void plz4cu_device_free(void* p) { if (p) cudaFree(p); }
+
+plz4cu_dict_t* plz4cu_dict_create(const void* d, size_t n)
+{
+    const uint8_t* b = static_cast<const uint8_t*>(d);
+    if (n > PLZ4CU_DICT_MAX) { b += n - PLZ4CU_DICT_MAX; n = PLZ4CU_DICT_MAX; }   // compress/dict.go:43-56
+    plz4cu_dict* dc = new plz4cu_dict();
+    dc->size = (uint32_t)n;
+    dc->h_bytes.assign(b, b + n);
+    if (n) {
+        // 16 bytes of slack so aligned-word reads near the end stay inside the allocation
+        cudaError_t e = cudaMalloc((void**)&dc->d_bytes, n + 16);
+        if (e == cudaSuccess) e = cudaMemcpy(dc->d_bytes, b, n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            fail(PLZ4CU_ERR_CUDA, "plz4cu_dict_create", e);
+            if (dc->d_bytes) cudaFree(dc->d_bytes);
+            delete dc;
+            return nullptr;
+        }
+    }
+    return dc;
+}
+void plz4cu_dict_destroy(plz4cu_dict_t* dc)
+{
+    if (!dc) return;
+    if (dc->d_bytes) cudaFree(dc->d_bytes);
+    delete dc;
+}
+
+int plz4cu_compress_batch_device(plz4cu_stream_t stream, const void* src_base, const uint64_t* src_off,
+                                 const uint32_t* src_len, uint32_t nblk, uint32_t dst_cap, int block_checksum,
+                                 int raw_blocks, const plz4cu_dict_t* dict, void* rec_base, uint32_t rec_stride,
+                                 uint32_t* rec_len)
+{
+    if (int r = ensure_configured()) return r;
+    if (nblk == 0) return 0;
+    if (!src_base || !src_off || !src_len || !rec_base || !rec_len) return fail(PLZ4CU_ERR_ARG, "compress_batch_device: null pointer");
+    if (rec_stride & 15u) return fail(PLZ4CU_ERR_ARG, "compress_batch_device: rec_stride must be a multiple of 16");
+    if ((reinterpret_cast<uintptr_t>(rec_base) & 15u) != 0) return fail(PLZ4CU_ERR_ARG, "compress_batch_device: rec_base must be 16-byte aligned");
+    if ((uint64_t)rec_stride < (uint64_t)dst_cap + (raw_blocks ? 0 : PLZ4CU_REC_OVERHEAD)) return fail(PLZ4CU_ERR_ARG, "compress_batch_device: rec_stride too small for dst_cap");
+    if (dict && dict->size) return fail(PLZ4CU_ERR_ARG, "compress_batch_device: dictionary compression not available in this build");
+    EncodeArgs a{};
+    a.src_base = static_cast<const uint8_t*>(src_base);
+    a.src_off = src_off; a.src_len = src_len; a.nblk = nblk; a.dst_cap = dst_cap;
+    a.block_checksum = block_checksum; a.raw_blocks = raw_blocks;
+    a.rec_base = static_cast<uint8_t*>(rec_base); a.rec_stride = rec_stride; a.rec_len = rec_len;
+    CU(launch_compress(a, static_cast<cudaStream_t>(stream)));
+    g_launches++;
+    return 0;
+}
+
+int plz4cu_decompress_batch_device(plz4cu_stream_t stream, const void* rec_base, const uint64_t* rec_off,
+                                   const uint32_t* raw_len, uint32_t nblk, uint32_t dst_cap, int verify_checksum,
+                                   int raw_blocks, const plz4cu_dict_t* dict, void* dst_base, uint64_t dst_stride,
+                                   int32_t* out_len)
+{
+    if (int r = ensure_configured()) return r;
+    if (nblk == 0) return 0;
+    if (!rec_base || !rec_off || !dst_base || !out_len) return fail(PLZ4CU_ERR_ARG, "decompress_batch_device: null pointer");
+    if (raw_blocks && !raw_len) return fail(PLZ4CU_ERR_ARG, "decompress_batch_device: raw_len required for raw blocks");
+    if (dst_stride < dst_cap) return fail(PLZ4CU_ERR_ARG, "decompress_batch_device: dst_stride < dst_cap");
+    DecodeArgs a{};
+    a.rec_base = static_cast<const uint8_t*>(rec_base);
+    a.rec_off = rec_off; a.raw_len = raw_len; a.nblk = nblk; a.dst_cap = dst_cap;
+    a.verify_checksum = verify_checksum; a.raw_blocks = raw_blocks;
+    a.dict = (dict && dict->size) ? dict->d_bytes : nullptr;
+    a.dict_size = dict ? dict->size : 0;
+    a.dst_base = static_cast<uint8_t*>(dst_base); a.dst_stride = dst_stride; a.out_len = out_len;
+    CU(launch_decompress(a, static_cast<cudaStream_t>(stream)));
+    g_launches++;
+    return 0;
+}
+
+int plz4cu_pack_records_device(plz4cu_stream_t stream, const void* rec_base, uint32_t rec_stride,
+                               const uint32_t* rec_len, uint32_t nblk, void* packed, uint64_t* packed_off)
+{
+    if (int r = ensure_configured()) return r;
+    if (!packed_off) return fail(PLZ4CU_ERR_ARG, "pack_records_device: null pointer");
+    CU(launch_pack(static_cast<const uint8_t*>(rec_base), rec_stride, rec_len, nblk,
+                   static_cast<uint8_t*>(packed), packed_off, static_cast<cudaStream_t>(stream)));
+    g_launches += nblk ? 2 : 1;
+    return 0;
+}
+
+int plz4cu_xxh32_batch_device(plz4cu_stream_t stream, const void* base, const uint64_t* off, const uint32_t* len,
+                              uint32_t nblk, uint32_t* out)
+{
+    if (int r = ensure_configured()) return r;
+    CU(launch_xxh32(static_cast<const uint8_t*>(base), off, len, nblk, out, static_cast<cudaStream_t>(stream)));
+    if (nblk) g_launches++;
+    return 0;
+}
+
+int plz4cu_gen_logtext_device(plz4cu_stream_t stream, uint32_t seed, uint64_t first_seg, void* dst, uint64_t n)
+{
+    if (int r = ensure_configured()) return r;
+    CU(launch_gen_logtext(seed, first_seg, static_cast<uint8_t*>(dst), n, static_cast<cudaStream_t>(stream)));
+    if (n) g_launches++;
+    return 0;
+}
+
+int plz4cu_gen_logtext_host(uint32_t seed, uint64_t first_seg, void* dst, uint64_t n)
+{
+    uint8_t* out = static_cast<uint8_t*>(dst);
+    for (uint64_t s = 0, pos = 0; pos < n; s++, pos += LOGTEXT_SEG) {
+        uint32_t len = (n - pos < LOGTEXT_SEG) ? (uint32_t)(n - pos) : LOGTEXT_SEG;
+        lt_fill_segment(seed, first_seg + s, out + pos, len);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- host-resident batches
+
+// Blocks are processed in chunks of roughly kChunkBytes of input, alternating between two lanes.
+static const uint64_t kChunkBytes = 64ull << 20;
+
+int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const uint32_t* src_len, uint32_t nblk,
+                               uint32_t dst_cap, int block_checksum, int raw_blocks, const plz4cu_dict_t* dict,
+                               void* packed, uint64_t packed_cap, uint64_t* packed_off)
+{
+    if (int r = ensure_configured()) return r;
+    if (!packed_off) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: null pointer");
+    packed_off[0] = 0;
+    if (nblk == 0) return 0;
+    if (!src || !src_off || !src_len || !packed) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: null pointer");
+    if (dict && dict->size) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: dictionary compression not available in this build");
+    Pipe* pp = pipe_for_current_device();
+    if (!pp) return fail(PLZ4CU_ERR_NODEVICE, "no CUDA device");
+    std::lock_guard<std::mutex> lk(pp->mu);
+    if (int r = pp->init()) return r;
+
+    const uint8_t* hsrc = static_cast<const uint8_t*>(src);
+    uint8_t* hout = static_cast<uint8_t*>(packed);
+    uint32_t max_len = 0;
+    for (uint32_t b = 0; b < nblk; b++) max_len = std::max(max_len, src_len[b]);
+    const uint32_t slot_payload = std::max(dst_cap, max_len);
+    const uint32_t stride = round_up16(slot_payload + (raw_blocks ? 0 : PLZ4CU_REC_OVERHEAD));
+
+    struct Chunk { uint32_t b0, b1; uint64_t lo, hi; };     // blocks [b0,b1), source byte span [lo,hi)
+    std::vector<Chunk> chunks;
+    for (uint32_t b = 0; b < nblk;) {
+        Chunk c{b, b, src_off[b], src_off[b] + src_len[b]};
+        while (c.b1 < nblk) {
+            uint64_t lo = std::min(c.lo, src_off[c.b1]), hi = std::max(c.hi, src_off[c.b1] + src_len[c.b1]);
+            if (c.b1 > c.b0 && hi - lo > kChunkBytes) break;
+            c.lo = lo; c.hi = hi; c.b1++;
+        }
+        chunks.push_back(c);
+        b = c.b1;
+    }
+
+    uint64_t out_pos = 0;
+    // software pipeline: issue chunk k on lane k&1, then drain chunk k-1
+    struct Pending { bool active = false; Chunk c; } pend[2];
+    auto drain = [&](int li) -> int {
+        Lane& L = pp->lane[li];
+        Pending& P = pend[li];
+        if (!P.active) return 0;
+        CU(cudaEventSynchronize(L.done));
+        const uint32_t cnt = P.c.b1 - P.c.b0;
+        const uint64_t* hoff = L.h_meta.as<uint64_t>();       // cnt+1 packed offsets, chunk-relative
+        const uint64_t total = hoff[cnt];
+        if (out_pos + total > packed_cap) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: packed buffer too small");
+        CU(cudaMemcpyAsync(hout + out_pos, L.packed.p, total, cudaMemcpyDeviceToHost, L.st));
+        for (uint32_t i = 0; i <= cnt; i++) packed_off[P.c.b0 + i] = out_pos + hoff[i];
+        out_pos += total;
+        CU(cudaStreamSynchronize(L.st));
+        P.active = false;
+        return 0;
+    };
+
+    for (size_t k = 0; k < chunks.size(); k++) {
+        const int li = (int)(k & 1);
+        if (int r = drain(li)) return r;
+        Lane& L = pp->lane[li];
+        const Chunk& c = chunks[k];
+        const uint32_t cnt = c.b1 - c.b0;
+        const uint64_t span = c.hi - c.lo;
+        CU(L.in.reserve(span + 16));
+        CU(L.out.reserve((uint64_t)cnt * stride));
+        CU(L.packed.reserve((uint64_t)cnt * stride));
+        CU(L.off.reserve((uint64_t)cnt * 8));
+        CU(L.len.reserve((uint64_t)cnt * 4));
+        CU(L.res.reserve((uint64_t)cnt * 4));
+        CU(L.poff.reserve((uint64_t)(cnt + 1) * 8));
+        CU(L.h_meta.reserve((uint64_t)(cnt + 1) * 8 + (uint64_t)cnt * 8));
+        uint64_t* h_rel = L.h_meta.as<uint64_t>() + (cnt + 1);   // second half: relative source offsets
+        for (uint32_t i = 0; i < cnt; i++) h_rel[i] = src_off[c.b0 + i] - c.lo;
+        CU(cudaMemcpyAsync(L.in.p, hsrc + c.lo, span, cudaMemcpyHostToDevice, L.st));
+        CU(cudaMemcpyAsync(L.off.p, h_rel, (uint64_t)cnt * 8, cudaMemcpyHostToDevice, L.st));
+        CU(cudaMemcpyAsync(L.len.p, src_len + c.b0, (uint64_t)cnt * 4, cudaMemcpyHostToDevice, L.st));
+        EncodeArgs a{};
+        a.src_base = L.in.as<uint8_t>(); a.src_off = L.off.as<uint64_t>(); a.src_len = L.len.as<uint32_t>();
+        a.nblk = cnt; a.dst_cap = dst_cap; a.block_checksum = block_checksum; a.raw_blocks = raw_blocks;
+        a.rec_base = L.out.as<uint8_t>(); a.rec_stride = stride; a.rec_len = L.res.as<uint32_t>();
+        CU(launch_compress(a, L.st));
+        CU(launch_pack(L.out.as<uint8_t>(), stride, L.res.as<uint32_t>(), cnt, L.packed.as<uint8_t>(), L.poff.as<uint64_t>(), L.st));
+        g_launches += 3;
+        CU(cudaMemcpyAsync(L.h_meta.p, L.poff.p, (uint64_t)(cnt + 1) * 8, cudaMemcpyDeviceToHost, L.st));
+        CU(cudaEventRecord(L.done, L.st));
+        pend[li].active = true; pend[li].c = c;
+    }
+    // drain in issue order
+    const int last = (int)((chunks.size() - 1) & 1);
+    if (int r = drain(last ^ 1)) return r;
+    if (int r = drain(last)) return r;
+    return 0;
+}
+
+int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const uint64_t* rec_off, const uint32_t* raw_len,
+                                 uint32_t nblk, uint32_t dst_cap, int verify_checksum, int raw_blocks,
+                                 const plz4cu_dict_t* dict, void* dst, uint64_t dst_stride, int32_t* out_len)
+{
+    if (int r = ensure_configured()) return r;
+    if (nblk == 0) return 0;
+    if (!recs || !rec_off || !dst || !out_len) return fail(PLZ4CU_ERR_ARG, "decompress_batch_host: null pointer");
+    if (raw_blocks && !raw_len) return fail(PLZ4CU_ERR_ARG, "decompress_batch_host: raw_len required for raw blocks");
+    if (dst_stride < dst_cap) return fail(PLZ4CU_ERR_ARG, "decompress_batch_host: dst_stride < dst_cap");
+    Pipe* pp = pipe_for_current_device();
+    if (!pp) return fail(PLZ4CU_ERR_NODEVICE, "no CUDA device");
+    std::lock_guard<std::mutex> lk(pp->mu);
+    if (int r = pp->init()) return r;
+
+    const uint8_t* hrec = static_cast<const uint8_t*>(recs);
+    uint8_t* hdst = static_cast<uint8_t*>(dst);
+
+    // extent of record b in the input: needs the size word on the frame path (host-side read)
+    auto rec_extent = [&](uint32_t b, uint64_t* lo, uint64_t* hi) -> int {
+        uint64_t o = rec_off[b];
+        if (raw_blocks) { *lo = o; *hi = o + raw_len[b]; }
+        else {
+            if (o + 4 > recs_bytes) return fail(PLZ4CU_ERR_ARG, "decompress_batch_host: record offset outside input");
+            uint32_t w; memcpy(&w, hrec + o, 4);
+            const uint64_t sz = (uint64_t)(w & 0x7FFFFFFFu);
+            *lo = o;
+            // an oversized size word is reported per block by the kernel from the word alone
+            *hi = (sz > dst_cap) ? o + 4 : o + 4 + sz + (verify_checksum ? 4 : 0);
+        }
+        if (*hi > recs_bytes) return fail(PLZ4CU_ERR_ARG, "decompress_batch_host: record runs past the input (short read)");
+        return 0;
+    };
+
+    struct Chunk { uint32_t b0, b1; uint64_t lo, hi; };
+    std::vector<Chunk> chunks;
+    const uint32_t max_blk_per_chunk = (uint32_t)std::max<uint64_t>(1, kChunkBytes / std::max<uint32_t>(dst_cap, 1));
+    for (uint32_t b = 0; b < nblk;) {
+        uint64_t lo, hi;
+        if (int r = rec_extent(b, &lo, &hi)) return r;
+        Chunk c{b, b + 1, lo, hi};
+        while (c.b1 < nblk && c.b1 - c.b0 < max_blk_per_chunk) {
+            uint64_t l2, h2;
+            if (int r = rec_extent(c.b1, &l2, &h2)) return r;
+            uint64_t nlo = std::min(c.lo, l2), nhi = std::max(c.hi, h2);
+            if (nhi - nlo > kChunkBytes) break;
+            c.lo = nlo; c.hi = nhi; c.b1++;
+        }
+        chunks.push_back(c);
+        b = c.b1;
+    }
+
+    struct Pending { bool active = false; Chunk c; } pend[2];
+    auto drain = [&](int li) -> int {
+        Lane& L = pp->lane[li];
+        Pending& P = pend[li];
+        if (!P.active) return 0;
+        CU(cudaStreamSynchronize(L.st));
+        P.active = false;
+        return 0;
+    };
+    for (size_t k = 0; k < chunks.size(); k++) {
+        const int li = (int)(k & 1);
+        if (int r = drain(li)) return r;
+        Lane& L = pp->lane[li];
+        const Chunk& c = chunks[k];
+        const uint32_t cnt = c.b1 - c.b0;
+        const uint64_t span = c.hi - c.lo;
+        const uint64_t dstride = ((uint64_t)dst_cap + 15u) & ~15ull;
+        CU(L.in.reserve(span + 16));
+        CU(L.out.reserve((uint64_t)cnt * dstride + 16));
+        CU(L.off.reserve((uint64_t)cnt * 8));
+        CU(L.len.reserve((uint64_t)cnt * 4));
+        CU(L.res.reserve((uint64_t)cnt * 4));
+        CU(L.h_meta.reserve((uint64_t)cnt * 8));
+        uint64_t* h_rel = L.h_meta.as<uint64_t>();
+        for (uint32_t i = 0; i < cnt; i++) h_rel[i] = rec_off[c.b0 + i] - c.lo;
+        CU(cudaMemcpyAsync(L.in.p, hrec + c.lo, span, cudaMemcpyHostToDevice, L.st));
+        CU(cudaMemcpyAsync(L.off.p, h_rel, (uint64_t)cnt * 8, cudaMemcpyHostToDevice, L.st));
+        if (raw_blocks) CU(cudaMemcpyAsync(L.len.p, raw_len + c.b0, (uint64_t)cnt * 4, cudaMemcpyHostToDevice, L.st));
+        DecodeArgs a{};
+        a.rec_base = L.in.as<uint8_t>(); a.rec_off = L.off.as<uint64_t>(); a.raw_len = L.len.as<uint32_t>();
+        a.nblk = cnt; a.dst_cap = dst_cap; a.verify_checksum = verify_checksum; a.raw_blocks = raw_blocks;
+        a.dict = (dict && dict->size) ? dict->d_bytes : nullptr; a.dict_size = dict ? dict->size : 0;
+        a.dst_base = L.out.as<uint8_t>(); a.dst_stride = dstride; a.out_len = L.res.as<int32_t>();
+        CU(launch_decompress(a, L.st));
+        g_launches++;
+        CU(cudaMemcpyAsync(out_len + c.b0, L.res.p, (uint64_t)cnt * 4, cudaMemcpyDeviceToHost, L.st));
+        if (dstride == dst_stride) {
+            CU(cudaMemcpyAsync(hdst + (uint64_t)c.b0 * dst_stride, L.out.p, (uint64_t)cnt * dstride, cudaMemcpyDeviceToHost, L.st));
+        } else {
+            CU(cudaMemcpy2DAsync(hdst + (uint64_t)c.b0 * dst_stride, dst_stride, L.out.p, dstride, dst_cap, cnt,
+                                 cudaMemcpyDeviceToHost, L.st));
+        }
+        pend[li].active = true; pend[li].c = c;
+    }
+    if (int r = drain(0)) return r;
+    if (int r = drain(1)) return r;
+    return 0;
+}
+
+// ---------------------------------------------------------------- per-block shims
+
+static int one_block_compress(const plz4cu_dict_t* dict, const void* src, int n, void* dst, int cap)
+{
+    if (n < 0 || (uint32_t)n > 0x7E000000u) return 0;
+    if (cap <= 0) return 0;
+    uint64_t off = 0, poff[2] = {0, 0};
+    uint32_t len = (uint32_t)n;
+    // LZ4_compress_fast never writes more than bound(n) bytes, so a larger cap changes nothing
+    uint32_t eff_cap = (uint32_t)std::min<uint64_t>((uint64_t)cap, plz4cu_compress_bound((size_t)n));
+    std::vector<uint8_t> tmp((size_t)eff_cap + 32);
+    uint8_t dummy = 0;
+    int r = plz4cu_compress_batch_host(n ? src : &dummy, &off, &len, 1, eff_cap, 0, 1, dict, tmp.data(), tmp.size(), poff);
+    if (r < 0) return INT32_MIN;
+    uint64_t c = poff[1] - poff[0];
+    if (c == 0 || c > (uint64_t)cap) return 0;
+    memcpy(dst, tmp.data(), c);
+    return (int)c;
+}
+
+int plz4cu_compress_fast(const void* src, int n, void* dst, int cap) { return one_block_compress(nullptr, src, n, dst, cap); }
+int plz4cu_compress_fast_dict(const plz4cu_dict_t* dict, const void* src, int n, void* dst, int cap)
+{
+    return one_block_compress(dict, src, n, dst, cap);
+}
+
+static int one_block_decompress(const plz4cu_dict_t* dict, const void* src, int n, void* dst, int cap)
+{
+    if (src == nullptr || cap < 0) return -1;     // lz4.c:2033
+    if (n < 0) return -1;
+    if (n == 0) {
+        // lz4.c:2064-2069: both special cases end in -1 for an empty input
+        return -1;
+    }
+    uint64_t off = 0;
+    uint32_t len = (uint32_t)n;
+    int32_t res = 0;
+    uint8_t dummy[16];
+    int r = plz4cu_decompress_batch_host(src, (uint64_t)n, &off, &len, 1, (uint32_t)cap, 0, 1, dict,
+                                         cap ? dst : dummy, (uint64_t)(cap ? cap : 16), &res);
+    if (r < 0) return INT32_MIN;
+    return res;
+}
+int plz4cu_decompress_safe(const void* src, int n, void* dst, int cap) { return one_block_decompress(nullptr, src, n, dst, cap); }
+int plz4cu_decompress_safe_dict(const plz4cu_dict_t* dict, const void* src, int n, void* dst, int cap)
+{
+    return one_block_decompress(dict, src, n, dst, cap);
+}
+
+}  // extern "C"

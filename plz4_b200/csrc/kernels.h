@@ -1,0 +1,56 @@
+// kernels.h — launch interfaces between the C-ABI layer (engine.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace plz4 {
+
+constexpr int32_t PLZ4CU_E_BLOCKHASH_ = -0x7F000001;
+constexpr int32_t PLZ4CU_E_OVERFLOW_ = -0x7F000002;
+
+constexpr int kDecodeThreads = 128;    // 4 warps = 4 blocks per CTA
+
+struct DecodeArgs {
+    const uint8_t* rec_base;
+    const uint64_t* rec_off;
+    const uint32_t* raw_len;      // raw_blocks only
+    uint32_t nblk;
+    uint32_t dst_cap;
+    int verify_checksum;
+    int raw_blocks;
+    const uint8_t* dict;          // last <=64 KiB of the dictionary, or nullptr
+    uint32_t dict_size;
+    uint8_t* dst_base;
+    uint64_t dst_stride;
+    int32_t* out_len;
+};
+cudaError_t launch_decompress(const DecodeArgs& a, cudaStream_t stream);
+
+struct EncodeArgs {
+    const uint8_t* src_base;
+    const uint64_t* src_off;
+    const uint32_t* src_len;
+    uint32_t nblk;
+    uint32_t dst_cap;
+    int block_checksum;
+    int raw_blocks;
+    const uint8_t* dict;          // dictionary bytes (device) or nullptr
+    uint32_t dict_size;
+    const uint16_t* dict_table;   // per-hash most recent dictionary position (device) or nullptr
+    uint8_t* rec_base;
+    uint32_t rec_stride;
+    uint32_t* rec_len;
+};
+cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream);
+cudaError_t configure_compress();     // one-time function attributes (opt-in shared memory)
+
+// dictionary table build (hash -> last position), device side
+cudaError_t launch_dict_build(const uint8_t* dict, uint32_t dict_size, uint16_t* table, cudaStream_t stream);
+
+cudaError_t launch_pack(const uint8_t* rec_base, uint32_t rec_stride, const uint32_t* rec_len, uint32_t nblk,
+                        uint8_t* packed, uint64_t* packed_off, cudaStream_t stream);
+cudaError_t launch_xxh32(const uint8_t* base, const uint64_t* off, const uint32_t* len, uint32_t nblk,
+                         uint32_t* out, cudaStream_t stream);
+cudaError_t launch_gen_logtext(uint32_t seed, uint64_t first_seg, uint8_t* dst, uint64_t n, cudaStream_t stream);
+
+}  // namespace plz4

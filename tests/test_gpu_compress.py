@@ -1,0 +1,79 @@
+"""GPU encode parity: every block the CUDA encoder emits is decoded byte-exactly by the reference
+decoder, framed exactly like blk.CompressToBlk, and within 3 % of liblz4's size."""
+import numpy as np
+import pytest
+
+from tests.datagen import KINDS, make
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 5, 12, 13, 14, 31, 32, 33, 64, 100, 1000, 4096, 65535, 65536]
+TOLERANCE = 1.03    # BASELINE.json north_star: compressed size within 3 % of liblz4 at the same level
+
+
+def test_golden_hello_and_empty(gpu):
+    assert gpu.compress_block(b"hello") == bytes.fromhex("5068656c6c6f")       # plz4_test.go:74 (G1)
+    assert gpu.compress_block(b"") == b"\x00"                                   # block_test.go:22-52 (G8)
+    assert gpu.decompress_block(bytes.fromhex("5068656c6c6f")) == b"hello"      # plz4_test.go:12
+    assert gpu.decompress_block(b"\x00") == b""
+
+
+def test_raw_blocks_decode_with_reference(gpu, codec):
+    srcs = [make(k, n) for k in KINDS for n in SIZES]
+    buf, off = b"".join(srcs), np.cumsum([0] + [len(s) for s in srcs])[:-1]
+    lens = [len(s) for s in srcs]
+    packed, poff = gpu.compress_batch(buf, off, lens, gpu.compress_block_bound(65536), raw_blocks=True)
+    for i, s in enumerate(srcs):
+        c = packed[int(poff[i]): int(poff[i + 1])].tobytes()
+        assert len(c) > 0
+        r, data = codec.decompress(c, len(s))          # exact capacity: enforces the end-of-block rules
+        assert r == len(s) and data == s, (i, r, len(s))
+        ref_c = codec.compress(s)
+        assert len(c) <= max(len(ref_c) * TOLERANCE, len(ref_c) + 8), (i, len(c), len(ref_c))
+
+
+@pytest.mark.parametrize("bsz", [65536, 262144, 4 << 20])
+@pytest.mark.parametrize("checksum", [False, True])
+def test_frame_records_layout(gpu, port, codec, bsz, checksum):
+    """Record bytes follow blk/blk.go:87-106: size word, stored bit, payload, xxh32 over the payload."""
+    kinds = ["log", "random", "zeros", "words", "runs", "record1025"]
+    blocks = [make(k, bsz) for k in kinds] + [make("log", 1000), make("random", 300), b"hello"]
+    buf, off = b"".join(blocks), np.cumsum([0] + [len(b) for b in blocks])[:-1]
+    packed, poff = gpu.compress_batch(buf, off, [len(b) for b in blocks], bsz, block_checksum=checksum)
+    tot_gpu = tot_ref = 0
+    for i, b in enumerate(blocks):
+        rec = packed[int(poff[i]): int(poff[i + 1])].tobytes()
+        word = int.from_bytes(rec[:4], "little")
+        n = word & 0x7FFFFFFF
+        assert len(rec) == 4 + n + (4 if checksum else 0)
+        payload = rec[4: 4 + n]
+        if checksum:
+            assert int.from_bytes(rec[4 + n:], "little") == port.xxh32(payload)
+        ref_rec = port.block_record(b, bsz, checksum)
+        ref_stored = bool(int.from_bytes(ref_rec[:4], "little") & 0x80000000)
+        if word & 0x80000000:
+            assert payload == b
+            assert ref_stored or len(ref_rec) >= len(b) * 0.97
+        else:
+            assert n <= bsz
+            r, data = codec.decompress(payload, bsz)
+            assert r == len(b) and data == b
+        tot_gpu += len(rec)
+        tot_ref += len(ref_rec)
+    assert tot_gpu <= tot_ref * TOLERANCE
+
+
+def test_logtext_ratio_vs_liblz4(gpu, codec):
+    """The benchmark workload itself: 64 x 64 KiB blocks of log text, total size within tolerance."""
+    from tests.datagen import logtext
+    bsz, nblk = 65536, 64
+    data = logtext(bsz * nblk)
+    off = np.arange(nblk, dtype=np.uint64) * bsz
+    packed, poff = gpu.compress_batch(data, off, [bsz] * nblk, bsz, block_checksum=True)
+    ref_total = sum(len(codec.compress(data[i * bsz:(i + 1) * bsz], bsz)) + 8 for i in range(nblk))
+    ratio = int(poff[nblk]) / ref_total
+    print(f"gpu/liblz4 size ratio on logtext: {ratio:.4f}")
+    assert ratio <= TOLERANCE
+    out, res = gpu.decompress_batch(packed, poff[:-1], bsz, verify_checksum=True)
+    assert (res == bsz).all()
+    assert out.reshape(-1).tobytes() == data
