@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's headline metric on its configs[1] workload.
+
+  metric   : LZ4 frame compress/decompress GB/s (uncompressed)
+  workload : synthetic log text, independent 64 KiB blocks, level 1, block checksums on,
+             no content checksum, device-resident; 8 GiB per GPU by default (weak scaling:
+             blocks are independent, ranks share nothing and there is no collective on the data path)
+  step     : one compress pass + one decompress pass over the whole workload
+  value    : uncompressed bytes through both passes / device time  (2*U / (t_c + t_d)), summed over ranks
+  e2e      : the same step through the host-buffer C ABI (plz4cu_*_batch_host) with pinned host
+             memory, H2D and D2H inside the timed region
+  roofline : the dominant kernel (lz4_compress_kernel): algorithmic bytes U + C' per launch over
+             its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference : the reference's own liblz4 (oracle/_ref, compiled from the
+             reference's vendored C) driven by a pthread fan-out over blocks on all host cores
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BSZ = 64 << 10
+SEED = 0x504C5A34
+METRIC = "LZ4 frame compress/decompress GB/s (uncompressed)"
+UNIT = "GB/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    """nvidia-smi sampled in the background DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU reference arm
+
+def cpu_reference(sample_bytes: int, steps: int, warmup: int, threads: int | None = None) -> dict:
+    """The reference's CPU path (oracle/_ref liblz4 when built, else the pinned port) on all host cores."""
+    import numpy as np
+    from oracle import oracle as O
+    from plz4_b200 import _lib
+    O.build()
+    port = O.Port()
+    drv = C.CDLL(os.path.join(ROOT, "oracle", "cpu_driver.so"))
+    drv.drv_compress_blocks.restype = C.c_int
+    drv.drv_compress_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    drv.drv_decompress_blocks.restype = C.c_int
+    drv.drv_decompress_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    if O.Ref.available():
+        ref = O.Ref()
+        kind = "reference"
+        cfn = C.cast(ref.lib.LZ4_compress_fast, C.c_void_p)
+        dfn = C.cast(ref.lib.LZ4_decompress_safe, C.c_void_p)
+    else:
+        kind = "port"
+        # adapters with liblz4's argument order live in the port library
+        cfn = C.cast(port.lib.orc_lz4_compress_fast, C.c_void_p)
+        dfn = C.cast(port.lib.orc_lz4_decompress_safe, C.c_void_p)
+    xfn = C.cast(port.lib.orc_xxh32, C.c_void_p)
+    threads = threads or os.cpu_count() or 1
+    nblk = max(1, sample_bytes // BSZ)
+    total = nblk * BSZ
+    src = np.empty(total, dtype=np.uint8)
+    _lib.lib().plz4cu_gen_logtext_host(SEED, 0, C.c_void_p(src.ctypes.data), total)   # host-only helper, no GPU
+    recs = np.empty(nblk * (BSZ + 8), dtype=np.uint8)
+    rec_len = np.zeros(nblk, dtype=np.uint32)
+    out = np.empty(total, dtype=np.uint8)
+    out_len = np.zeros(nblk, dtype=np.uint32)
+    rec_off = (np.arange(nblk, dtype=np.uint64) * (BSZ + 8))
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    tc = td = 0.0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        drv.drv_compress_blocks(cfn, xfn, vp(src), total, BSZ, 1, vp(recs), vp(rec_len), threads)
+        t1 = time.perf_counter()
+        errs = drv.drv_decompress_blocks(dfn, xfn, vp(recs), vp(rec_off), vp(rec_len), nblk, BSZ, 1, vp(out), vp(out_len), threads)
+        t2 = time.perf_counter()
+        if errs:
+            raise RuntimeError("cpu baseline: decode errors")
+        if it >= warmup:
+            tc += t1 - t0
+            td += t2 - t1
+    assert bytes(out[:4096]) == bytes(src[:4096])
+    csize = int(rec_len.sum())
+    return {
+        "kind": kind, "cores": threads, "sample": f"{total >> 20} MiB logtext, 64 KiB blocks, block checksums, {steps} passes",
+        "value": 2 * total * steps / (tc + td) / 1e9, "unit": UNIT,
+        "compress_gbs": total * steps / tc / 1e9, "decompress_gbs": total * steps / td / 1e9,
+        "ratio": csize / total, "ms_per_step": (tc + td) / steps * 1e3, "bytes": total,
+    }
+
+
+def run_reference(args) -> None:
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    r = cpu_reference(args.cpu_sample_mib << 20, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(r["value"], 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, r["bytes"]),
+        "compress_gbs": round(r["compress_gbs"], 4), "decompress_gbs": round(r["decompress_gbs"], 4),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": round(r["value"], 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, nbytes_per_gpu: int) -> dict:
+    return {
+        "workload": "BASELINE configs[1]: synthetic log text, independent 64 KiB blocks, level 1, "
+                    "block checksums, no content checksum, device-resident",
+        "bytes_per_gpu": int(nbytes_per_gpu), "block_size": BSZ, "blocks_per_gpu": int(nbytes_per_gpu // BSZ),
+        "level": 1, "block_checksum": True, "content_checksum": False, "seed": hex(SEED),
+        "step": "compress pass + decompress pass over all blocks",
+        "l2": "inputs (GiBs) far exceed the 126 MB L2; no flush needed",
+        "parallelism": f"{args.gpus} x independent block shards, no collective",
+    }
+
+
+# ------------------------------------------------------------------ GPU arm
+
+def run_gpu(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from plz4_b200 import _lib
+    from plz4_b200._lib import check
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    check(L.plz4cu_init(local), "plz4cu_init")
+
+    nbytes = int(args.gib * (1 << 30)) // BSZ * BSZ
+    nblk = nbytes // BSZ
+    stride = BSZ + 16
+    stream = torch.cuda.current_stream()
+    sh = C.c_void_p(stream.cuda_stream)
+    u8 = lambda n: torch.empty(n, dtype=torch.uint8, device=dev)
+    src, recs, out = u8(nbytes), u8(nblk * stride), u8(nbytes)
+    src_off = torch.arange(nblk, dtype=torch.int64, device=dev) * BSZ
+    src_len = torch.full((nblk,), BSZ, dtype=torch.int32, device=dev)
+    rec_off = torch.arange(nblk, dtype=torch.int64, device=dev) * stride
+    rec_len = torch.zeros(nblk, dtype=torch.int32, device=dev)
+    out_len = torch.zeros(nblk, dtype=torch.int32, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    # every rank gets its own slice of the stream: segments [rank*nblk, (rank+1)*nblk)
+    check(L.plz4cu_gen_logtext_device(sh, SEED, rank * nblk, p(src), nbytes), "gen_logtext")
+    torch.cuda.synchronize()
+
+    def compress():
+        check(L.plz4cu_compress_batch_device(sh, p(src), p(src_off), p(src_len), nblk, BSZ, 1, 0, None,
+                                             p(recs), stride, p(rec_len)), "compress_batch_device")
+
+    def decompress():
+        check(L.plz4cu_decompress_batch_device(sh, p(recs), p(rec_off), None, nblk, BSZ, 1, 0, None,
+                                               p(out), BSZ, p(out_len)), "decompress_batch_device")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        compress()
+        decompress()
+    barrier()
+    # correctness gate inside the bench: the round trip must be exact and every block decoded
+    assert bool((out_len == BSZ).all()), "decode failed"
+    assert torch.equal(out, src), "round trip mismatch"
+    csize = int(rec_len.to(torch.int64).sum())      # C' = framed compressed bytes (size word + payload + xxh32)
+
+    sampler = ClockSampler(local)
+    launches0 = L.plz4cu_launch_count()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        ev[k][0].record(stream)
+        compress()
+        ev[k][1].record(stream)
+        decompress()
+        ev[k][2].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = L.plz4cu_launch_count() - launches0
+    tc = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
+    td = sum(e[1].elapsed_time(e[2]) for e in ev) / 1e3
+    tt = ev[0][0].elapsed_time(ev[-1][2]) / 1e3
+
+    # ---- e2e through the host-buffer C ABI (pinned host memory; H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        e_bytes = min(nbytes, int(args.e2e_gib * (1 << 30)) // BSZ * BSZ)
+        e_blk = e_bytes // BSZ
+        h_src = torch.empty(e_bytes, dtype=torch.uint8).pin_memory()
+        h_src.copy_(src[:e_bytes])
+        h_packed = torch.empty(e_blk * (BSZ + 8), dtype=torch.uint8).pin_memory()
+        h_out = torch.empty(e_bytes, dtype=torch.uint8).pin_memory()
+        h_off = np.arange(e_blk, dtype=np.uint64) * BSZ
+        h_len = np.full(e_blk, BSZ, dtype=np.uint32)
+        h_poff = np.zeros(e_blk + 1, dtype=np.uint64)
+        h_res = np.zeros(e_blk, dtype=np.int32)
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        hp = lambda t: C.c_void_p(t.data_ptr())
+
+        def e2e_step():
+            check(L.plz4cu_compress_batch_host(hp(h_src), vp(h_off), vp(h_len), e_blk, BSZ, 1, 0, None,
+                                               hp(h_packed), h_packed.numel(), vp(h_poff)), "compress_batch_host")
+            check(L.plz4cu_decompress_batch_host(hp(h_packed), int(h_poff[e_blk]), vp(h_poff), None, e_blk, BSZ, 1, 0, None,
+                                                 hp(h_out), BSZ, vp(h_res)), "decompress_batch_host")
+        for _ in range(max(1, min(args.warmup, 3))):
+            e2e_step()
+        assert (h_res == BSZ).all() and torch.equal(h_out, h_src), "e2e round trip mismatch"
+        barrier()
+        t0 = time.perf_counter()
+        e_steps = max(1, args.steps)
+        for _ in range(e_steps):
+            e2e_step()
+        barrier()
+        te = time.perf_counter() - t0
+        c_e = int(h_poff[e_blk])
+        e2e = {"t": te, "steps": e_steps, "bytes": e_bytes,
+               "h2d": e_bytes + c_e + e_blk * 24, "d2h": c_e + e_bytes + e_blk * 12 + 8}
+        del h_src, h_packed, h_out
+
+    # ---- max over ranks, sum of work
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    tt_max, tc_max, td_max = allmax(tt), allmax(tc), allmax(td)
+    te_max = allmax(e2e["t"]) if e2e else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = float(json.load(f)["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        pass
+    K = args.steps
+    value = world * 2 * nbytes * K / tt_max / 1e9
+    algo = nbytes + csize                       # per launch: U read + C' written (compress); C' read + U written (decompress)
+    c_ach = algo / (tc / K) / 1e9
+    d_ach = algo / (td / K) / 1e9
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": round(tt_max / K * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": workload_config(args, nbytes),
+        "compress_gbs": round(world * nbytes * K / tc_max / 1e9, 3),
+        "decompress_gbs": round(world * nbytes * K / td_max / 1e9, 3),
+        "compressed_ratio": round(csize / nbytes, 5),
+        "roofline": {"bound": "hbm", "kernel": "lz4_compress_kernel", "achieved": round(c_ach, 2), "peak": peaks, "unit": "GB/s",
+                     "frac": round(c_ach / peaks, 5), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo, "launch_ms": round(tc / K * 1e3, 3)},
+        "roofline_decompress": {"bound": "hbm", "kernel": "lz4_decompress_kernel", "achieved": round(d_ach, 2), "peak": peaks,
+                                "unit": "GB/s", "frac": round(d_ach / peaks, 5), "traffic": None,
+                                "algorithmic_bytes_per_launch": algo, "launch_ms": round(td / K * 1e3, 3)},
+        "gpu_launches": int(launches), "clocks": clocks, "wall_s": round(t_wall, 3),
+    }
+    if e2e:
+        line["e2e"] = {"value": round(world * 2 * e2e["bytes"] * e2e["steps"] / te_max / 1e9, 3), "unit": UNIT,
+                       "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                       "bytes_per_gpu": int(e2e["bytes"]), "steps": e2e["steps"],
+                       "api": "plz4cu_compress_batch_host + plz4cu_decompress_batch_host, pinned host buffers"}
+    if not args.no_cpu:
+        try:
+            r = cpu_reference(args.cpu_sample_mib << 20, 3, 1)
+            line["cpu_baseline"] = {k: (round(r[k], 4) if isinstance(r[k], float) else r[k])
+                                    for k in ("value", "unit", "cores", "kind", "sample", "compress_gbs", "decompress_gbs", "ratio")}
+        except Exception as e:        # the baseline is a reported number, never a reason to lose the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="plz4_b200", choices=["plz4_b200", "reference"])
+    ap.add_argument("--gib", type=float, default=8.0, help="uncompressed GiB per GPU (configs[1] = 8)")
+    ap.add_argument("--e2e-gib", type=float, default=4.0, help="GiB per GPU pushed through the host-buffer API per step")
+    ap.add_argument("--cpu-sample-mib", type=int, default=2048, help="bounded sample for the CPU baseline / reference arm")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl != "reference" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -503,3 +503,16 @@ ORC_API int orc_block_record(const orc_dict_t* dc, const uint8_t* src, int n, in
     }
     return c + 4;
 }
+
+/* ------------------------------------------------------------------ liblz4-shaped adapters
+ * Same argument order as LZ4_compress_fast / LZ4_decompress_safe so oracle/cpu_driver.c can time
+ * the port through the very function-pointer types it uses for oracle/_ref/libreflz4.so. */
+ORC_API int orc_lz4_compress_fast(const char* src, char* dst, int n, int cap, int accel)
+{
+    (void)accel;
+    return orc_compress_fast((const uint8_t*)src, n, (uint8_t*)dst, cap);
+}
+ORC_API int orc_lz4_decompress_safe(const char* src, char* dst, int n, int cap)
+{
+    return orc_decompress_safe((const uint8_t*)src, n, (uint8_t*)dst, cap);
+}
