@@ -7,7 +7,7 @@
 //   compress/decompress.go:32-38,46-58 -> clz4.go:47-78 -> lz4.c:2023-2445 LZ4_decompress_generic
 //
 // Accept/reject behaviour and the negative return code follow liblz4's decode_full_block state
-// machine exactly (derivation: DESIGN.md "decoder state machine"; CPU statement: oracle/lz4_port.c).
+// machine exactly (derivation: DESIGN.md "decoder state machine").
 //
 // Work split inside the warp: the sequence parse is warp-uniform (every lane reads the same token /
 // offset bytes, which the LSU serves as one broadcast), the byte movement is lane-parallel.  A match
