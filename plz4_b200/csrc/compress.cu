@@ -10,11 +10,15 @@
 //       in flight), looks every one up in a per-warp shared-memory table and resolves same-group
 //       duplicates with match.any, so each position sees its most recent earlier occurrence (what
 //       liblz4's mutating table gives it one position at a time); then EVERY lane measures its own
-//       candidate in parallel — two aligned 16-byte loads of the candidate, own bytes from the
-//       neighbours' registers by shuffle — giving a match length of up to 16 and a backward byte, then
-//   (b) walks the measured candidates greedily with no memory access on the common path: first
-//       match at/after the anchor wins; only matches longer than 16 go back to memory; short
-//       sequences (the common case) leave the warp as a single predicated byte store.
+//       candidate in parallel — two aligned 16-byte loads around the candidate, own bytes from the
+//       neighbours' registers by shuffle — giving a match length of up to 15, a backward byte and a
+//       one-step-lazy hint, then
+//   (b) walks the measured candidates with no memory access on the common path (only matches longer
+//       than 15 go back to memory), and emits ALL sequences of the group at once: sizes are
+//       prefix-summed across lanes, match-start lanes store token / offset / length byte, literal
+//       lanes store their own byte.
+// The table holds the low 16 bits of positions: LZ4's window is 64 KiB, so that is enough for any
+// block size (a stale entry aliases into the window and is caught by the byte comparison).
 // The output is a valid LZ4 block obeying the end-of-block rules liblz4's decoder enforces
 // (last match starts <= n-12 and ends <= n-5, lz4.c:245-246,963-964); bytes differ from liblz4's,
 // size stays within the tolerance pinned by tests/test_gpu_compress.py.
@@ -26,6 +30,8 @@
 namespace plz4 {
 
 constexpr int kEncodeWarps = 4;                 // blocks per CTA
+__constant__ int g_back_dev = 1;                // tuning knobs (see configure_compress)
+__constant__ int g_jump_dev = 64;
 __constant__ int g_lazy_dev = 1;                // 0 = greedy; k>0 = take p+1 if its match is longer by >= k
 
 // bytes needed for the 255-run extension of a length whose nibble saturated
@@ -38,7 +44,7 @@ __device__ __forceinline__ void put_ext(uint8_t* o, int rest, int lane)
 }
 
 // Long-match tail: equal bytes of src[a..] vs src[b..] with a < limit, 32 per ballot.
-__device__ __forceinline__ int count_equal(const uint8_t* __restrict__ src, int a, int b, int limit, int lane)
+__device__ __noinline__ int count_equal(const uint8_t* __restrict__ src, int a, int b, int limit, int lane)
 {
     int total = 0;
     for (;;) {
@@ -50,7 +56,7 @@ __device__ __forceinline__ int count_equal(const uint8_t* __restrict__ src, int 
     }
 }
 
-// General (rare) sequence emit: literal run >= 15 or match >= 19.
+// General (rare) sequence emit: literal run >= 15 or match >= 274.
 __device__ __noinline__ int emit_long(uint8_t* o, const uint8_t* __restrict__ lits, int lit, uint32_t off, int mlen, int lane)
 {
     const int mrest = mlen - MINMATCH - 15;
@@ -65,18 +71,20 @@ __device__ __noinline__ int emit_long(uint8_t* o, const uint8_t* __restrict__ li
     return w;
 }
 
-template <typename TabT, int kHashBits>
+template <int kHashBits>
 __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int n, uint8_t* dst,
-                                            int cap, TabT* table, int lane)
+                                            int cap, uint16_t* table, int lane)
 {
-    constexpr TabT kEmpty = (TabT)~(TabT)0;
-    constexpr int kProbe = 16;                       // bytes of every candidate examined in parallel
+    constexpr uint32_t kEmpty = 0xFFFFu;
+    constexpr int kProbe = 15;                       // bytes of every candidate examined in parallel
+    const int kJumpAt = g_jump_dev;
     const bool kLazy = g_lazy_dev != 0;
     const uint32_t kLazyGain = (uint32_t)g_lazy_dev - 1u;
+    const bool kBack = g_back_dev != 0;
     {
         uint4 fill = make_uint4(~0u, ~0u, ~0u, ~0u);
         uint4* t4 = reinterpret_cast<uint4*>(table);
-        constexpr int kVecs = (int)(sizeof(TabT) << kHashBits) / 16;
+        constexpr int kVecs = (2 << kHashBits) / 16;
         for (int i = lane; i < kVecs; i += 32) t4[i] = fill;
     }
     __syncwarp();
@@ -86,135 +94,199 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
         const int mf_end = n - MFLIMIT + 1;          // a match may start at p < mf_end
         const int match_end = n - LASTLITERALS;      // and must end at or before match_end
         const int ld_end = n - 3;                    // 4 bytes can be read at q < ld_end
-        const uintptr_t src_end = reinterpret_cast<uintptr_t>(src + n);
+        // 32-bit addressing relative to aligned bases: byte q of src is byte (d16+q) of src16
+        const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+        const uint4* __restrict__ src16 = reinterpret_cast<const uint4*>(sa & ~uintptr_t(15));
+        const uint32_t* __restrict__ src4 = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(15));
+        const uint32_t d16 = (uint32_t)sa & 15u;
+        const uint32_t end16 = (d16 + (uint32_t)n + 15u) >> 4;       // 16-byte chunks holding valid bytes
+        const uint32_t last4 = (d16 + (uint32_t)n - 1u) >> 2;        // last word holding a valid byte
+        auto own4 = [&](int q) -> uint32_t {                          // 4 bytes at position q (q < ld_end)
+            const uint32_t a = d16 + (uint32_t)q;
+            const uint32_t lo = src4[a >> 2], hi = src4[min((a >> 2) + 1u, last4)];
+            return __funnelshift_r(lo, hi, (a & 3u) * 8u);
+        };
         int base = 0;
-        uint32_t v_cur = (lane < ld_end) ? load_u32_unaligned(src + lane) : 0u;
-        uint32_t v_nxt = (lane + 32 < ld_end) ? load_u32_unaligned(src + lane + 32) : 0u;
-        uint32_t tail_byte = 0;                      // byte at base-1 (only meaningful when base advanced by 32)
+        uint32_t v_prv = 0;                          // previous group's bytes (valid whenever literals carry over)
+        uint32_t v_cur = (lane < ld_end) ? own4(lane) : 0u;
+        uint32_t v_nxt = (lane + 32 < ld_end) ? own4(lane + 32) : 0u;
         while (base < mf_end) {
             const int p = base + lane;
             const bool valid = p < mf_end;
             const uint32_t v = v_cur;
             // bytes two groups ahead go in flight now; they are consumed at the bottom of the loop
-            const uint32_t v_far = (p + 64 < ld_end) ? load_u32_unaligned(src + p + 64) : 0u;
+            const uint32_t v_far = (p + 64 < ld_end) ? own4(p + 64) : 0u;
 
             // ---- (a1) hash, table lookup, same-group duplicates, table update
             uint32_t h = 0x80000000u | (uint32_t)lane;
             int cand = -1;
             if (valid) {
                 h = (v * 2654435761u) >> (32 - kHashBits);
-                TabT c = table[h];
-                if (c != kEmpty) cand = (int)c;
+                const uint32_t c = table[h];
+                int q = (int)(((uint32_t)p & 0xFFFF0000u) | c);
+                if (q >= p) q -= 65536;
+                if (c != kEmpty) cand = q;
             }
             const uint32_t same = __match_any_sync(FULL_MASK, h);
             const uint32_t lower = same & ((1u << lane) - 1u);
             if (lower) cand = base + 31 - __clz(lower);
-            if (valid && (same >> lane) == 1u) table[h] = (TabT)p;   // most recent occurrence wins
+            if (valid && (same >> lane) == 1u) table[h] = (uint16_t)p;   // most recent occurrence wins
             __syncwarp();
 
-            // ---- (a2) every lane measures its own candidate: 16 bytes forwards, 1 byte backwards.
-            // positions already covered by the previous match were inserted above but need no candidate
-            const bool want = valid && p >= anchor && cand >= 0 && (uint32_t)(p - cand) <= MAX_DISTANCE;
+            // ---- (a2) every lane measures its own candidate: 1 byte backwards, 15 bytes forwards.
+            // positions already covered by the previous match were inserted above but need no candidate;
+            // candidate 0 is skipped so that the byte before the candidate always exists.
+            const bool want = valid && p >= anchor && cand >= 1 && (uint32_t)(p - cand) <= MAX_DISTANCE;
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-            uint32_t cback = 0x100;                  // never equals a byte
             uint32_t t = 0;
             if (want) {
-                const uintptr_t ca = reinterpret_cast<uintptr_t>(src + cand);
-                const uint4* q = reinterpret_cast<const uint4*>(ca & ~uintptr_t(15));
-                t = (uint32_t)ca & 15u;
-                r0 = q[0];
-                if (reinterpret_cast<uintptr_t>(q + 1) < src_end) r1 = q[1];
-                if (cand > 0) cback = src[cand - 1];
+                const uint32_t ca = d16 + (uint32_t)cand - 1u;       // fetch starts at the byte before the candidate
+                const uint32_t ci = ca >> 4;
+                t = ca & 15u;
+                r0 = src16[ci];
+                if (ci + 1 < end16) r1 = src16[ci + 1];
             }
-            // own bytes p+4 .. p+15 come from the neighbours' registers
-            uint32_t o1, o2, o3;
+            // own bytes p-1 .. p+14 as four words, from the neighbours' registers
+            uint32_t o0, o1, o2, o3;
             {
-                const int s1 = lane + 4, s2 = lane + 8, s3 = lane + 12;
-                const uint32_t a1 = __shfl_sync(FULL_MASK, v_cur, s1 & 31), b1 = __shfl_sync(FULL_MASK, v_nxt, s1 & 31);
-                const uint32_t a2 = __shfl_sync(FULL_MASK, v_cur, s2 & 31), b2 = __shfl_sync(FULL_MASK, v_nxt, s2 & 31);
-                const uint32_t a3 = __shfl_sync(FULL_MASK, v_cur, s3 & 31), b3 = __shfl_sync(FULL_MASK, v_nxt, s3 & 31);
+                const uint32_t up = __shfl_up_sync(FULL_MASK, v_cur, 1);
+                o0 = lane ? up : (v_cur << 8);                        // lane 0: no backward byte
+                const int s1 = lane + 3, s2 = lane + 7, s3 = lane + 11;
+                const uint32_t a1 = __shfl_sync(FULL_MASK, v_cur, s1), b1 = __shfl_sync(FULL_MASK, v_nxt, s1);
+                const uint32_t a2 = __shfl_sync(FULL_MASK, v_cur, s2), b2 = __shfl_sync(FULL_MASK, v_nxt, s2);
+                const uint32_t a3 = __shfl_sync(FULL_MASK, v_cur, s3), b3 = __shfl_sync(FULL_MASK, v_nxt, s3);
                 o1 = (s1 < 32) ? a1 : b1; o2 = (s2 < 32) ? a2 : b2; o3 = (s3 < 32) ? a3 : b3;
             }
-            uint32_t oback = __shfl_up_sync(FULL_MASK, v_cur, 1) & 0xFFu;
-            if (lane == 0) oback = tail_byte;
-            const uint32_t next_tail = __shfl_sync(FULL_MASK, v_cur, 31) & 0xFFu;
-
             int eqlen;
+            bool backeq;
             {
-                // barrel-select the 5 words that hold candidate bytes t .. t+19 of the 32 fetched
+                // barrel-select the 5 words that hold fetched bytes t .. t+19
                 const bool w1 = (t & 4u) != 0, w2 = (t & 8u) != 0;
                 const uint32_t T0 = w1 ? r0.y : r0.x, T1 = w1 ? r0.z : r0.y, T2 = w1 ? r0.w : r0.z, T3 = w1 ? r1.x : r0.w,
                                T4 = w1 ? r1.y : r1.x, T5 = w1 ? r1.z : r1.y, T6 = w1 ? r1.w : r1.z;
                 const uint32_t S0 = w2 ? T2 : T0, S1 = w2 ? T3 : T1, S2 = w2 ? T4 : T2, S3 = w2 ? T5 : T3, S4 = w2 ? T6 : T4;
                 const uint32_t bs = (t & 3u) * 8u;
-                const uint32_t x0 = __funnelshift_r(S0, S1, bs) ^ v;
+                const uint32_t x0 = __funnelshift_r(S0, S1, bs) ^ o0;
                 const uint32_t x1 = __funnelshift_r(S1, S2, bs) ^ o1;
                 const uint32_t x2 = __funnelshift_r(S2, S3, bs) ^ o2;
                 const uint32_t x3 = __funnelshift_r(S3, S4, bs) ^ o3;
-                // first differing byte: ctz(x)>>3, and ctz(0) == 32 conveniently means "all four equal"
-                const int b0 = __clz(__brev(x0)) >> 3, b1 = __clz(__brev(x1)) >> 3;
-                const int b2 = __clz(__brev(x2)) >> 3, b3 = __clz(__brev(x3)) >> 3;
-                const int tail = (b2 < 4) ? b2 : 4 + b3;
-                const int mid = (b1 < 4) ? b1 : 4 + tail;
-                eqlen = (b0 < 4) ? b0 : 4 + mid;
+                backeq = (x0 & 0xFFu) == 0;
+                // first differing forward byte: pick the first non-zero word, then ctz>>3 (ctz(0)==32 -> 4)
+                const uint32_t y0 = x0 >> 8;
+                const bool z0 = y0 == 0, z1 = x1 == 0, z2 = x2 == 0;
+                const uint32_t xs = z0 ? (z1 ? (z2 ? x3 : x2) : x1) : y0;
+                const int skip = z0 ? (z1 ? (z2 ? 11 : 7) : 3) : 0;
+                eqlen = skip + (__clz(__brev(xs)) >> 3);
                 const int room = match_end - p;
                 if (eqlen > room) eqlen = room;
             }
             const bool ok = want && eqlen >= MINMATCH;
             const bool more = ok && eqlen == kProbe && p + kProbe < match_end;
-            const bool backok = ok && p > anchor && oback == cback;
-            // one word per lane for the greedy walk: offset | length | flags
-            const uint32_t pack = ((uint32_t)(p - cand) << 16) | ((uint32_t)eqlen << 8) | (backok ? 2u : 0u) | (more ? 1u : 0u);
-            uint32_t bal = __ballot_sync(FULL_MASK, ok);
+            const bool backok = kBack && ok && lane > 0 && backeq;
+            const uint32_t bal = __ballot_sync(FULL_MASK, ok);
+            // one-step lazy hint: the next position holds a strictly longer match
+            const int nxt_len = __shfl_down_sync(FULL_MASK, eqlen, 1);
+            const bool lazy = kLazy && ok && lane < 31 && ((bal >> (lane + 1)) & 1u) && (uint32_t)nxt_len > (uint32_t)eqlen + kLazyGain;
+            // one word per lane for the walk: offset | length | flags
+            const uint32_t pack = ((uint32_t)(p - cand) << 16) | ((uint32_t)eqlen << 8) | (lazy ? 4u : 0u) | (backok ? 2u : 0u) | (more ? 1u : 0u);
 
-            // ---- (b) greedy walk over the verified candidates: no loads unless a match is long
-            while (bal) {
-                int f = __ffs(bal) - 1;
+            // ---- (b1) selection: registers only, except matches longer than kProbe
+            uint32_t starts = 0;                 // bit s: a chosen match starts at base+s
+            int my_mlen = 0;                     // on start lanes: final match length
+            uint32_t my_off = 0;                 //                 and offset
+            int pos = anchor > base ? anchor - base : 0;      // first lane not covered yet (may be >= 32)
+            uint32_t rem = (pos >= 32) ? 0u : (bal & (0xFFFFFFFFu << pos));
+            while (rem) {
+                int f = __ffs(rem) - 1;
                 uint32_t pk = __shfl_sync(FULL_MASK, pack, f);
-                if (kLazy && f < 31) {
-                    // one-step lazy parse: a strictly longer match one byte later beats this one
-                    const uint32_t pk1 = __shfl_sync(FULL_MASK, pack, f + 1);
-                    if (((bal >> (f + 1)) & 1u) && ((pk1 >> 8) & 0xFFu) > ((pk >> 8) & 0xFFu) + kLazyGain) { f++; pk = pk1 & ~2u; }
-                }
-                int mpos = base + f;
+                if (pk & 4u) { f++; pk = __shfl_sync(FULL_MASK, pack, f) & ~2u; }
                 const uint32_t off = pk >> 16;
                 int mlen = (int)((pk >> 8) & 0xFFu);
-                if (pk & 1u) mlen += count_equal(src, mpos + kProbe, mpos - (int)off + kProbe, match_end, lane);
-                if ((pk & 2u) && mpos > anchor) {
-                    mpos--; mlen++;
-                    while (mpos > anchor && mpos - (int)off > 0 && src[mpos - 1] == src[mpos - (int)off - 1]) { mpos--; mlen++; }
-                }
-                const int lit = mpos - anchor;
-                uint8_t* o = dst + op;
-                if (lit < 15 && mlen < 19) {
-                    // whole sequence = token + lit literals + offset <= 17 bytes: one store per lane
-                    const int need = lit + 3;
-                    if (op + need > cap) return 0;
-                    uint32_t byte;
-                    if (lane == 0) byte = (uint32_t)((lit << 4) | (mlen - MINMATCH));
-                    else if (lane <= lit) byte = src[anchor + lane - 1];
-                    else byte = (lane == lit + 1) ? off : (off >> 8);
-                    if (lane < need) o[lane] = (uint8_t)byte;
-                    op += need;
-                } else {
-                    const int mrest = mlen - MINMATCH - 15;
-                    const int need = 1 + (lit >= 15 ? ext_bytes(lit - 15) : 0) + lit + 2 + (mrest >= 0 ? ext_bytes(mrest) : 0);
-                    if (op + need > cap) return 0;
-                    op += emit_long(o, src + anchor, lit, off, mlen, lane);
-                }
-                anchor = mpos + mlen;
-                const int d = anchor - base;
-                bal = (d >= 32) ? 0u : (bal & ~((1u << d) - 1u));
+                if (pk & 1u) mlen += count_equal(src, base + f + kProbe, base + f - (int)off + kProbe, match_end, lane);
+                const int s = ((pk & 2u) && f > pos) ? f - 1 : f;       // one byte backwards into the literals
+                mlen += f - s;
+                if (lane == s) { my_mlen = mlen; my_off = off; }
+                starts |= 1u << s;
+                pos = s + mlen;
+                rem = (pos >= 32) ? 0u : (rem & (0xFFFFFFFFu << pos));
             }
-            if (anchor > base + 32) {
+
+            if (starts) {
+                // ---- (b2) emit every chosen sequence of the group at once
+                const bool is_start = (starts >> lane) & 1u;
+                const uint32_t below = starts & ((1u << lane) - 1u);
+                const int g = 31 - __clz(below | 1u);
+                const int prev_end = __shfl_sync(FULL_MASK, lane + my_mlen, g);
+                const int P = below ? prev_end : (anchor - base);        // end of the previous match, lane units (may be < 0)
+                const int lit = lane - P;
+                const bool fits = !is_start || (lit < 15 && my_mlen < 19 + 255);
+                uint8_t* o = dst + op;
+                if (__all_sync(FULL_MASK, fits)) {
+                    const int xb = (my_mlen >= 19) ? 1 : 0;
+                    const int size = is_start ? (3 + lit + xb) : 0;
+                    int incl = size;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int up = __shfl_up_sync(FULL_MASK, incl, d);
+                        if (lane >= d) incl += up;
+                    }
+                    const int O = incl - size;
+                    const int T = __shfl_sync(FULL_MASK, incl, 31);
+                    if (op + T > cap) return 0;
+                    if (is_start) {
+                        const int ml = my_mlen - MINMATCH;
+                        uint8_t* os = o + O;
+                        os[0] = (uint8_t)((lit << 4) | (ml < 15 ? ml : 15));
+                        os += lit;
+                        os[1] = (uint8_t)my_off;
+                        os[2] = (uint8_t)(my_off >> 8);
+                        if (xb) os[3] = (uint8_t)(ml - 15);
+                    }
+                    // literal bytes of this group: uncovered lanes that have a chosen match above them
+                    const uint32_t atbelow = starts & ((2u << lane) - 1u);
+                    const int ps = 31 - __clz(atbelow | 1u);
+                    const int ps_len = __shfl_sync(FULL_MASK, my_mlen, ps);
+                    const bool covered = (atbelow && lane < ps + ps_len) || (lane < anchor - base);
+                    const uint32_t above = starts & ~((2u << lane) - 1u);
+                    const int ns = __ffs(above) - 1;
+                    const uint32_t where = __shfl_sync(FULL_MASK, (uint32_t)(O + 65 - P), ns);   // O + 1 - P, kept positive
+                    if (!covered && above) o[(int)where - 64 + lane] = (uint8_t)v_cur;
+                    // literals carried over from the previous group belong to the first sequence (O == 0)
+                    const int nc = base - anchor;
+                    if (nc > 0) {
+                        const uint32_t cb = __shfl_sync(FULL_MASK, v_prv, 32 - nc + lane);
+                        if (lane < nc) o[1 + lane] = (uint8_t)cb;
+                    }
+                    op += T;
+                } else {
+                    // rare: a literal run >= 15 or a match >= 274 in this group: one sequence at a time
+                    uint32_t st = starts;
+                    int a = anchor;
+                    while (st) {
+                        const int s = __ffs(st) - 1;
+                        st &= st - 1;
+                        const int mlen = __shfl_sync(FULL_MASK, my_mlen, s);
+                        const uint32_t off = __shfl_sync(FULL_MASK, my_off, s);
+                        const int mpos = base + s;
+                        const int l = mpos - a;
+                        const int mrest = mlen - MINMATCH - 15;
+                        const int need = 1 + (l >= 15 ? ext_bytes(l - 15) : 0) + l + 2 + (mrest >= 0 ? ext_bytes(mrest) : 0);
+                        if (op + need > cap) return 0;
+                        op += emit_long(dst + op, src + a, l, off, mlen, lane);
+                        a = mpos + mlen;
+                    }
+                }
+                anchor = base + pos;
+            }
+            if (anchor >= base + kJumpAt) {
                 base = anchor;          // a long match skipped whole groups: their positions are not inserted
-                v_cur = (base + lane < ld_end) ? load_u32_unaligned(src + base + lane) : 0u;
-                v_nxt = (base + lane + 32 < ld_end) ? load_u32_unaligned(src + base + lane + 32) : 0u;
+                v_cur = (base + lane < ld_end) ? own4(base + lane) : 0u;
+                v_nxt = (base + lane + 32 < ld_end) ? own4(base + lane + 32) : 0u;
             } else {
                 base += 32;
+                v_prv = v_cur;
                 v_cur = v_nxt;
                 v_nxt = v_far;
-                tail_byte = next_tail;
             }
         }
     }
@@ -234,11 +306,11 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
 }
 
 template <int kHashBits>
-__global__ void __launch_bounds__(kEncodeWarps * 32)
+__global__ void __launch_bounds__(kEncodeWarps * 32, 6)
 lz4_compress_kernel(EncodeArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kTableBytes = 2 << kHashBits;      // u16[1<<bits] (n <= 64 KiB) or u32[1<<(bits-1)]
+    constexpr int kTableBytes = 2 << kHashBits;      // u16[1 << bits]
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const uint32_t b = blockIdx.x * kEncodeWarps + warp;
@@ -248,11 +320,9 @@ lz4_compress_kernel(EncodeArgs a)
     const int n = (int)a.src_len[b];
     uint8_t* rec = a.rec_base + (uint64_t)b * a.rec_stride;
     uint8_t* payload = a.raw_blocks ? rec : rec + 4;
-    void* table = smem + warp * kTableBytes;
+    uint16_t* table = reinterpret_cast<uint16_t*>(smem + warp * kTableBytes);
 
-    int c;
-    if (n <= 65536) c = encode_block<uint16_t, kHashBits>(src, n, payload, (int)a.dst_cap, (uint16_t*)table, lane);
-    else            c = encode_block<uint32_t, kHashBits - 1>(src, n, payload, (int)a.dst_cap, (uint32_t*)table, lane);
+    int c = encode_block<kHashBits>(src, n, payload, (int)a.dst_cap, table, lane);
 
     if (a.raw_blocks) {
         if (lane == 0) a.rec_len[b] = (uint32_t)c;      // 0 = does not fit (clz4.go:40-42)
@@ -280,36 +350,51 @@ lz4_compress_kernel(EncodeArgs a)
 static int g_hash_bits = 12;     // 8 KiB of table per warp: twice the resident warps of liblz4's 13 bits; the one-step
                                  // lazy parse more than pays the ratio back (profiles/r01_sweep.txt)
 
+template <int kBits>
+static cudaError_t set_smem_attr()
+{
+    return cudaFuncSetAttribute(lz4_compress_kernel<kBits>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kEncodeWarps * (2 << kBits));
+}
+
 cudaError_t configure_compress()
 {
-    if (const char* e = getenv("PLZ4CU_HASH_BITS")) {          // tuning knob: 12 halves the table (more warps/SM)
+    // tuning knobs for experiments; the defaults are the product configuration
+    if (const char* e = getenv("PLZ4CU_HASH_BITS")) {
         int v = atoi(e);
         if (v >= 11 && v <= 13) g_hash_bits = v;
+    }
+    if (const char* e = getenv("PLZ4CU_BACK")) {
+        int v = atoi(e);
+        cudaError_t err = cudaMemcpyToSymbol(g_back_dev, &v, sizeof v);
+        if (err != cudaSuccess) return err;
+    }
+    if (const char* e = getenv("PLZ4CU_JUMP")) {
+        int v = atoi(e);
+        cudaError_t err = cudaMemcpyToSymbol(g_jump_dev, &v, sizeof v);
+        if (err != cudaSuccess) return err;
     }
     if (const char* e = getenv("PLZ4CU_LAZY")) {
         int v = atoi(e);
         cudaError_t err = cudaMemcpyToSymbol(g_lazy_dev, &v, sizeof v);
         if (err != cudaSuccess) return err;
     }
-    {
-        cudaError_t err = cudaFuncSetAttribute(lz4_compress_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               kEncodeWarps * (2 << 11));
-        if (err != cudaSuccess) return err;
-    }
-    cudaError_t err = cudaFuncSetAttribute(lz4_compress_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kEncodeWarps * (2 << 13));
-    if (err != cudaSuccess) return err;
-    return cudaFuncSetAttribute(lz4_compress_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kEncodeWarps * (2 << 12));
+    cudaError_t err = set_smem_attr<11>();
+    if (err == cudaSuccess) err = set_smem_attr<12>();
+    if (err == cudaSuccess) err = set_smem_attr<13>();
+    return err;
 }
 
 cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
 {
     if (a.nblk == 0) return cudaSuccess;
     dim3 grid((a.nblk + kEncodeWarps - 1) / kEncodeWarps), block(kEncodeWarps * 32);
-    if (g_hash_bits == 11) lz4_compress_kernel<11><<<grid, block, kEncodeWarps * (2 << 11), stream>>>(a);
-    else if (g_hash_bits == 12) lz4_compress_kernel<12><<<grid, block, kEncodeWarps * (2 << 12), stream>>>(a);
-    else                   lz4_compress_kernel<13><<<grid, block, kEncodeWarps * (2 << 13), stream>>>(a);
+    // blocks above 64 KiB come in small numbers (64 per 256 MiB at 4 MiB): occupancy is not the limit there,
+    // so they get liblz4's 8192-entry table back
+    const int bits = (a.dst_cap > 65536u + 65536u / 255u + 16u) ? 13 : g_hash_bits;
+    if (bits == 11)      lz4_compress_kernel<11><<<grid, block, kEncodeWarps * (2 << 11), stream>>>(a);
+    else if (bits == 12) lz4_compress_kernel<12><<<grid, block, kEncodeWarps * (2 << 12), stream>>>(a);
+    else                        lz4_compress_kernel<13><<<grid, block, kEncodeWarps * (2 << 13), stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -92,14 +92,16 @@ struct HostBuf {
 struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
-    DevBuf in, out, packed, off, len, res, poff;
-    HostBuf h_meta;      // pinned staging for small metadata
+    DevBuf in, out, packed, off, res, poff;
+    HostBuf h_meta, h_res;      // pinned staging for small metadata (up / down)
 };
+
+constexpr int kLanes = 3;
 
 struct Pipe {
     std::mutex mu;
     int device = -1;
-    Lane lane[2];
+    Lane lane[kLanes];
     bool ready = false;
     int init()
     {
@@ -300,9 +302,17 @@ int plz4cu_gen_logtext_host(uint32_t seed, uint64_t first_seg, void* dst, uint64
 }
 
 // ---------------------------------------------------------------- host-resident batches
+//
+// Blocks are cut into chunks of roughly kChunkBytes of input and software-pipelined over kLanes
+// lanes (stream + private scratch each), so that the H2D of chunk k, the kernels of chunk k-1 and
+// the D2H of chunk k-2 overlap.  All small metadata crosses PCIe through pinned staging, so no call
+// in the loop blocks the host except the two explicit waits.
 
-// Blocks are processed in chunks of roughly kChunkBytes of input, alternating between two lanes.
-static const uint64_t kChunkBytes = 64ull << 20;
+static const uint64_t kChunkBytes = 32ull << 20;
+
+namespace {
+struct Chunk { uint32_t b0, b1; uint64_t lo, hi; };     // blocks [b0,b1), input byte span [lo,hi)
+}
 
 int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const uint32_t* src_len, uint32_t nblk,
                                uint32_t dst_cap, int block_checksum, int raw_blocks, const plz4cu_dict_t* dict,
@@ -326,7 +336,6 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
     const uint32_t slot_payload = std::max(dst_cap, max_len);
     const uint32_t stride = round_up16(slot_payload + (raw_blocks ? 0 : PLZ4CU_REC_OVERHEAD));
 
-    struct Chunk { uint32_t b0, b1; uint64_t lo, hi; };     // blocks [b0,b1), source byte span [lo,hi)
     std::vector<Chunk> chunks;
     for (uint32_t b = 0; b < nblk;) {
         Chunk c{b, b, src_off[b], src_off[b] + src_len[b]};
@@ -338,63 +347,67 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         chunks.push_back(c);
         b = c.b1;
     }
-
+    const int nchunks = (int)chunks.size();
     uint64_t out_pos = 0;
-    // software pipeline: issue chunk k on lane k&1, then drain chunk k-1
-    struct Pending { bool active = false; Chunk c; } pend[2];
-    auto drain = [&](int li) -> int {
-        Lane& L = pp->lane[li];
-        Pending& P = pend[li];
-        if (!P.active) return 0;
-        CU(cudaEventSynchronize(L.done));
-        const uint32_t cnt = P.c.b1 - P.c.b0;
-        const uint64_t* hoff = L.h_meta.as<uint64_t>();       // cnt+1 packed offsets, chunk-relative
-        const uint64_t total = hoff[cnt];
-        if (out_pos + total > packed_cap) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: packed buffer too small");
-        CU(cudaMemcpyAsync(hout + out_pos, L.packed.p, total, cudaMemcpyDeviceToHost, L.st));
-        for (uint32_t i = 0; i <= cnt; i++) packed_off[P.c.b0 + i] = out_pos + hoff[i];
-        out_pos += total;
-        CU(cudaStreamSynchronize(L.st));
-        P.active = false;
-        return 0;
-    };
 
-    for (size_t k = 0; k < chunks.size(); k++) {
-        const int li = (int)(k & 1);
-        if (int r = drain(li)) return r;
-        Lane& L = pp->lane[li];
+    // stage 1: inputs up, kernels, packed offsets down
+    auto issue = [&](int k) -> int {
+        Lane& L = pp->lane[k % kLanes];
         const Chunk& c = chunks[k];
         const uint32_t cnt = c.b1 - c.b0;
         const uint64_t span = c.hi - c.lo;
         CU(L.in.reserve(span + 16));
         CU(L.out.reserve((uint64_t)cnt * stride));
         CU(L.packed.reserve((uint64_t)cnt * stride));
-        CU(L.off.reserve((uint64_t)cnt * 8));
-        CU(L.len.reserve((uint64_t)cnt * 4));
+        CU(L.off.reserve((uint64_t)cnt * 12));
         CU(L.res.reserve((uint64_t)cnt * 4));
         CU(L.poff.reserve((uint64_t)(cnt + 1) * 8));
-        CU(L.h_meta.reserve((uint64_t)(cnt + 1) * 8 + (uint64_t)cnt * 8));
-        uint64_t* h_rel = L.h_meta.as<uint64_t>() + (cnt + 1);   // second half: relative source offsets
-        for (uint32_t i = 0; i < cnt; i++) h_rel[i] = src_off[c.b0 + i] - c.lo;
+        CU(L.h_meta.reserve((uint64_t)cnt * 12));
+        CU(L.h_res.reserve((uint64_t)(cnt + 1) * 8));
+        uint64_t* h_rel = L.h_meta.as<uint64_t>();
+        uint32_t* h_len = reinterpret_cast<uint32_t*>(h_rel + cnt);
+        for (uint32_t i = 0; i < cnt; i++) { h_rel[i] = src_off[c.b0 + i] - c.lo; h_len[i] = src_len[c.b0 + i]; }
         CU(cudaMemcpyAsync(L.in.p, hsrc + c.lo, span, cudaMemcpyHostToDevice, L.st));
-        CU(cudaMemcpyAsync(L.off.p, h_rel, (uint64_t)cnt * 8, cudaMemcpyHostToDevice, L.st));
-        CU(cudaMemcpyAsync(L.len.p, src_len + c.b0, (uint64_t)cnt * 4, cudaMemcpyHostToDevice, L.st));
+        CU(cudaMemcpyAsync(L.off.p, h_rel, (uint64_t)cnt * 12, cudaMemcpyHostToDevice, L.st));
         EncodeArgs a{};
-        a.src_base = L.in.as<uint8_t>(); a.src_off = L.off.as<uint64_t>(); a.src_len = L.len.as<uint32_t>();
+        a.src_base = L.in.as<uint8_t>(); a.src_off = L.off.as<uint64_t>();
+        a.src_len = reinterpret_cast<const uint32_t*>(L.off.as<uint64_t>() + cnt);
         a.nblk = cnt; a.dst_cap = dst_cap; a.block_checksum = block_checksum; a.raw_blocks = raw_blocks;
         a.rec_base = L.out.as<uint8_t>(); a.rec_stride = stride; a.rec_len = L.res.as<uint32_t>();
         CU(launch_compress(a, L.st));
         CU(launch_pack(L.out.as<uint8_t>(), stride, L.res.as<uint32_t>(), cnt, L.packed.as<uint8_t>(), L.poff.as<uint64_t>(), L.st));
         g_launches += 3;
-        CU(cudaMemcpyAsync(L.h_meta.p, L.poff.p, (uint64_t)(cnt + 1) * 8, cudaMemcpyDeviceToHost, L.st));
+        CU(cudaMemcpyAsync(L.h_res.p, L.poff.p, (uint64_t)(cnt + 1) * 8, cudaMemcpyDeviceToHost, L.st));
         CU(cudaEventRecord(L.done, L.st));
-        pend[li].active = true; pend[li].c = c;
+        return 0;
+    };
+    // stage 2: once the sizes are known on the host, bring the packed records down
+    auto post = [&](int k) -> int {
+        Lane& L = pp->lane[k % kLanes];
+        const Chunk& c = chunks[k];
+        const uint32_t cnt = c.b1 - c.b0;
+        CU(cudaEventSynchronize(L.done));
+        const uint64_t* hoff = L.h_res.as<uint64_t>();
+        const uint64_t total = hoff[cnt];
+        if (out_pos + total > packed_cap) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: packed buffer too small");
+        CU(cudaMemcpyAsync(hout + out_pos, L.packed.p, total, cudaMemcpyDeviceToHost, L.st));
+        for (uint32_t i = 0; i <= cnt; i++) packed_off[c.b0 + i] = out_pos + hoff[i];
+        out_pos += total;
+        return 0;
+    };
+    auto finish = [&](int k) -> int {
+        CU(cudaStreamSynchronize(pp->lane[k % kLanes].st));
+        return 0;
+    };
+    int rc = 0;
+    for (int k = 0; k < nchunks && !rc; k++) {
+        if (k >= kLanes) rc = finish(k - kLanes);
+        if (!rc) rc = issue(k);
+        if (!rc && k >= 1) rc = post(k - 1);
     }
-    // drain in issue order
-    const int last = (int)((chunks.size() - 1) & 1);
-    if (int r = drain(last ^ 1)) return r;
-    if (int r = drain(last)) return r;
-    return 0;
+    if (!rc) rc = post(nchunks - 1);
+    for (int k = std::max(0, nchunks - kLanes); k < nchunks; k++) { int r2 = finish(k); if (!rc) rc = r2; }
+    return rc;
 }
 
 int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const uint64_t* rec_off, const uint32_t* raw_len,
@@ -430,7 +443,6 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
         return 0;
     };
 
-    struct Chunk { uint32_t b0, b1; uint64_t lo, hi; };
     std::vector<Chunk> chunks;
     const uint32_t max_blk_per_chunk = (uint32_t)std::max<uint64_t>(1, kChunkBytes / std::max<uint32_t>(dst_cap, 1));
     for (uint32_t b = 0; b < nblk;) {
@@ -447,54 +459,56 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
         chunks.push_back(c);
         b = c.b1;
     }
+    const int nchunks = (int)chunks.size();
+    const uint64_t dstride = ((uint64_t)dst_cap + 15u) & ~15ull;
 
-    struct Pending { bool active = false; Chunk c; } pend[2];
-    auto drain = [&](int li) -> int {
-        Lane& L = pp->lane[li];
-        Pending& P = pend[li];
-        if (!P.active) return 0;
-        CU(cudaStreamSynchronize(L.st));
-        P.active = false;
-        return 0;
-    };
-    for (size_t k = 0; k < chunks.size(); k++) {
-        const int li = (int)(k & 1);
-        if (int r = drain(li)) return r;
-        Lane& L = pp->lane[li];
+    auto issue = [&](int k) -> int {
+        Lane& L = pp->lane[k % kLanes];
         const Chunk& c = chunks[k];
         const uint32_t cnt = c.b1 - c.b0;
         const uint64_t span = c.hi - c.lo;
-        const uint64_t dstride = ((uint64_t)dst_cap + 15u) & ~15ull;
         CU(L.in.reserve(span + 16));
         CU(L.out.reserve((uint64_t)cnt * dstride + 16));
-        CU(L.off.reserve((uint64_t)cnt * 8));
-        CU(L.len.reserve((uint64_t)cnt * 4));
+        CU(L.off.reserve((uint64_t)cnt * 12));
         CU(L.res.reserve((uint64_t)cnt * 4));
-        CU(L.h_meta.reserve((uint64_t)cnt * 8));
+        CU(L.h_meta.reserve((uint64_t)cnt * 12));
+        CU(L.h_res.reserve((uint64_t)cnt * 4));
         uint64_t* h_rel = L.h_meta.as<uint64_t>();
-        for (uint32_t i = 0; i < cnt; i++) h_rel[i] = rec_off[c.b0 + i] - c.lo;
+        uint32_t* h_len = reinterpret_cast<uint32_t*>(h_rel + cnt);
+        for (uint32_t i = 0; i < cnt; i++) { h_rel[i] = rec_off[c.b0 + i] - c.lo; h_len[i] = raw_blocks ? raw_len[c.b0 + i] : 0u; }
         CU(cudaMemcpyAsync(L.in.p, hrec + c.lo, span, cudaMemcpyHostToDevice, L.st));
-        CU(cudaMemcpyAsync(L.off.p, h_rel, (uint64_t)cnt * 8, cudaMemcpyHostToDevice, L.st));
-        if (raw_blocks) CU(cudaMemcpyAsync(L.len.p, raw_len + c.b0, (uint64_t)cnt * 4, cudaMemcpyHostToDevice, L.st));
+        CU(cudaMemcpyAsync(L.off.p, h_rel, (uint64_t)cnt * 12, cudaMemcpyHostToDevice, L.st));
         DecodeArgs a{};
-        a.rec_base = L.in.as<uint8_t>(); a.rec_off = L.off.as<uint64_t>(); a.raw_len = L.len.as<uint32_t>();
+        a.rec_base = L.in.as<uint8_t>(); a.rec_off = L.off.as<uint64_t>();
+        a.raw_len = reinterpret_cast<const uint32_t*>(L.off.as<uint64_t>() + cnt);
         a.nblk = cnt; a.dst_cap = dst_cap; a.verify_checksum = verify_checksum; a.raw_blocks = raw_blocks;
         a.dict = (dict && dict->size) ? dict->d_bytes : nullptr; a.dict_size = dict ? dict->size : 0;
         a.dst_base = L.out.as<uint8_t>(); a.dst_stride = dstride; a.out_len = L.res.as<int32_t>();
         CU(launch_decompress(a, L.st));
         g_launches++;
-        CU(cudaMemcpyAsync(out_len + c.b0, L.res.p, (uint64_t)cnt * 4, cudaMemcpyDeviceToHost, L.st));
+        CU(cudaMemcpyAsync(L.h_res.p, L.res.p, (uint64_t)cnt * 4, cudaMemcpyDeviceToHost, L.st));
         if (dstride == dst_stride) {
             CU(cudaMemcpyAsync(hdst + (uint64_t)c.b0 * dst_stride, L.out.p, (uint64_t)cnt * dstride, cudaMemcpyDeviceToHost, L.st));
         } else {
             CU(cudaMemcpy2DAsync(hdst + (uint64_t)c.b0 * dst_stride, dst_stride, L.out.p, dstride, dst_cap, cnt,
                                  cudaMemcpyDeviceToHost, L.st));
         }
-        pend[li].active = true; pend[li].c = c;
+        return 0;
+    };
+    auto finish = [&](int k) -> int {
+        Lane& L = pp->lane[k % kLanes];
+        const Chunk& c = chunks[k];
+        CU(cudaStreamSynchronize(L.st));
+        memcpy(out_len + c.b0, L.h_res.p, (size_t)(c.b1 - c.b0) * 4);
+        return 0;
+    };
+    int rc = 0;
+    for (int k = 0; k < nchunks && !rc; k++) {
+        if (k >= kLanes) rc = finish(k - kLanes);
+        if (!rc) rc = issue(k);
     }
-    if (int r = drain(0)) return r;
-    if (int r = drain(1)) return r;
-    return 0;
+    for (int k = std::max(0, nchunks - kLanes); k < nchunks; k++) { int r2 = finish(k); if (!rc) rc = r2; }
+    return rc;
 }
 
 // ---------------------------------------------------------------- per-block shims

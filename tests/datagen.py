@@ -1,6 +1,7 @@
 """Seeded test inputs shared by the CPU and GPU suites."""
 import ctypes as C
 import random
+import zlib
 
 import numpy as np
 
@@ -14,7 +15,7 @@ def logtext(nbytes: int, seed: int = 0x504C5A34, first_seg: int = 0) -> bytes:
 
 
 def make(kind: str, n: int, seed: int = 1) -> bytes:
-    rng = random.Random((hash(kind) & 0xFFFF) * 1000003 + seed * 7919 + n)
+    rng = random.Random((zlib.crc32(kind.encode()) & 0xFFFF) * 1000003 + seed * 7919 + n)
     if kind == "random":
         return rng.randbytes(n)
     if kind == "zeros":
