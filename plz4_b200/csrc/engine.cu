@@ -10,6 +10,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -41,8 +42,24 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess)
         if (e__ != cudaSuccess) return fail(PLZ4CU_ERR_CUDA, #call, e__); \
     } while (0)
 
+// host pipeline tunables (see "host-resident batches" below)
+constexpr int kMaxLanes = 8;
+int kLanes = 4;                                  // lanes in use                   (PLZ4CU_LANES)
+uint32_t kChunkBlocks = 2048;                    // blocks per chunk we aim for    (PLZ4CU_CHUNK_BLOCKS)
+const uint64_t kChunkBytes = 512ull << 20;       // upper bound on a chunk's input span
+
+void read_tuning_env()
+{
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (const char* e = getenv("PLZ4CU_LANES")) { int v = atoi(e); if (v >= 1 && v <= kMaxLanes) kLanes = v; }
+        if (const char* e = getenv("PLZ4CU_CHUNK_BLOCKS")) { int v = atoi(e); if (v >= 1) kChunkBlocks = (uint32_t)v; }
+    });
+}
+
 int ensure_configured()
 {
+    read_tuning_env();
     // per-device function attributes must be set on every device we run on
     static std::mutex mu;
     static std::vector<int> done;
@@ -96,12 +113,12 @@ struct Lane {
     HostBuf h_meta, h_res;      // pinned staging for small metadata (up / down)
 };
 
-constexpr int kLanes = 3;
+
 
 struct Pipe {
     std::mutex mu;
     int device = -1;
-    Lane lane[kLanes];
+    Lane lane[kMaxLanes];
     bool ready = false;
     int init()
     {
@@ -303,12 +320,14 @@ int plz4cu_gen_logtext_host(uint32_t seed, uint64_t first_seg, void* dst, uint64
 
 // ---------------------------------------------------------------- host-resident batches
 //
-// Blocks are cut into chunks of roughly kChunkBytes of input and software-pipelined over kLanes
-// lanes (stream + private scratch each), so that the H2D of chunk k, the kernels of chunk k-1 and
-// the D2H of chunk k-2 overlap.  All small metadata crosses PCIe through pinned staging, so no call
-// in the loop blocks the host except the two explicit waits.
+// Blocks are cut into chunks and software-pipelined over kLanes lanes (stream + private scratch
+// each), so that the H2D of chunk k, the kernels of chunk k-1 and the D2H of chunk k-2 overlap.
+// A chunk must hold enough blocks to fill the GPU on its own — one warp works on one block for
+// milliseconds, so a launch with fewer blocks than resident warps (148 SMs x 24..36) runs at a
+// fraction of the kernel's throughput — hence the block-count target, capped by bytes.
+// All small metadata crosses PCIe through pinned staging, so no call in the loop blocks the host
+// except the explicit waits.
 
-static const uint64_t kChunkBytes = 32ull << 20;
 
 namespace {
 struct Chunk { uint32_t b0, b1; uint64_t lo, hi; };     // blocks [b0,b1), input byte span [lo,hi)
@@ -341,7 +360,7 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         Chunk c{b, b, src_off[b], src_off[b] + src_len[b]};
         while (c.b1 < nblk) {
             uint64_t lo = std::min(c.lo, src_off[c.b1]), hi = std::max(c.hi, src_off[c.b1] + src_len[c.b1]);
-            if (c.b1 > c.b0 && hi - lo > kChunkBytes) break;
+            if (c.b1 > c.b0 && (hi - lo > kChunkBytes || c.b1 - c.b0 >= kChunkBlocks)) break;
             c.lo = lo; c.hi = hi; c.b1++;
         }
         chunks.push_back(c);
@@ -399,13 +418,15 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         CU(cudaStreamSynchronize(pp->lane[k % kLanes].st));
         return 0;
     };
-    int rc = 0;
+    // chunk j is issued at step j, its packed bytes are requested at step j + kLanes - 1 (so kLanes - 1 younger
+    // chunks keep the GPU busy while the host waits for j's sizes), and its lane is recycled at step j + kLanes
+    int rc = 0, posted = 0;
     for (int k = 0; k < nchunks && !rc; k++) {
         if (k >= kLanes) rc = finish(k - kLanes);
         if (!rc) rc = issue(k);
-        if (!rc && k >= 1) rc = post(k - 1);
+        if (!rc && k >= kLanes - 1) { rc = post(k - (kLanes - 1)); posted = k - (kLanes - 1) + 1; }
     }
-    if (!rc) rc = post(nchunks - 1);
+    for (; posted < nchunks && !rc; posted++) rc = post(posted);
     for (int k = std::max(0, nchunks - kLanes); k < nchunks; k++) { int r2 = finish(k); if (!rc) rc = r2; }
     return rc;
 }
@@ -444,7 +465,7 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
     };
 
     std::vector<Chunk> chunks;
-    const uint32_t max_blk_per_chunk = (uint32_t)std::max<uint64_t>(1, kChunkBytes / std::max<uint32_t>(dst_cap, 1));
+    const uint32_t max_blk_per_chunk = (uint32_t)std::min<uint64_t>(kChunkBlocks, std::max<uint64_t>(1, kChunkBytes / std::max<uint32_t>(dst_cap, 1)));
     for (uint32_t b = 0; b < nblk;) {
         uint64_t lo, hi;
         if (int r = rec_extent(b, &lo, &hi)) return r;
