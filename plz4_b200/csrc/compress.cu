@@ -43,13 +43,13 @@ __device__ __forceinline__ void put_ext(uint8_t* o, int rest, int lane)
     for (int k = lane; k < nb; k += 32) o[k] = (k == nb - 1) ? (uint8_t)(rest - 255 * (nb - 1)) : (uint8_t)255;
 }
 
-// Long-match tail: equal bytes of src[a..] vs src[b..] with a < limit, 32 per ballot.
-__device__ __noinline__ int count_equal(const uint8_t* __restrict__ src, int a, int b, int limit, int lane)
+// Long-match tail: number of equal bytes of a[0..] and b[0..], at most `limit`, 32 per ballot.
+__device__ __noinline__ int count_equal(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int limit, int lane)
 {
     int total = 0;
     for (;;) {
-        int k = a + total + lane;
-        bool eq = (k < limit) && (src[k] == src[b + total + lane]);
+        int k = total + lane;
+        bool eq = (k < limit) && (a[k] == b[k]);
         uint32_t ne = __ballot_sync(FULL_MASK, !eq);
         if (ne) return total + (__ffs(ne) - 1);
         total += 32;
@@ -71,9 +71,13 @@ __device__ __noinline__ int emit_long(uint8_t* o, const uint8_t* __restrict__ li
     return w;
 }
 
-template <int kHashBits>
+// kDict: the block may reference a read-only dictionary (a4: compress/indie.go:14-35, clz4.go:160-179).
+// Positions then live in a virtual space where the dictionary ends at 65536 and the block starts there;
+// the table starts as a copy of the dictionary's table instead of empty.
+template <int kHashBits, bool kDict>
 __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int n, uint8_t* dst,
-                                            int cap, uint16_t* table, int lane)
+                                            int cap, uint16_t* table, int lane,
+                                            const uint8_t* __restrict__ dict, int dsz, const uint16_t* __restrict__ dict_table)
 {
     constexpr uint32_t kEmpty = 0xFFFFu;
     constexpr int kProbe = 15;                       // bytes of every candidate examined in parallel
@@ -84,10 +88,12 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
     {
         uint4 fill = make_uint4(~0u, ~0u, ~0u, ~0u);
         uint4* t4 = reinterpret_cast<uint4*>(table);
+        const uint4* d4 = reinterpret_cast<const uint4*>(dict_table);
         constexpr int kVecs = (2 << kHashBits) / 16;
-        for (int i = lane; i < kVecs; i += 32) t4[i] = fill;
+        for (int i = lane; i < kVecs; i += 32) t4[i] = kDict ? d4[i] : fill;
     }
     __syncwarp();
+    constexpr int kVirt = kDict ? 65536 : 0;          // virtual position of block byte 0
 
     int op = 0, anchor = 0;
     if (n >= MFLIMIT + 1) {
@@ -106,6 +112,9 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             const uint32_t lo = src4[a >> 2], hi = src4[min((a >> 2) + 1u, last4)];
             return __funnelshift_r(lo, hi, (a & 3u) * 8u);
         };
+        const uintptr_t da = reinterpret_cast<uintptr_t>(dict);
+        const uint4* __restrict__ dict16 = reinterpret_cast<const uint4*>(da & ~uintptr_t(15));
+        const uint32_t dd16 = (uint32_t)da & 15u;
         int base = 0;
         uint32_t v_prv = 0;                          // previous group's bytes (valid whenever literals carry over)
         uint32_t v_cur = (lane < ld_end) ? own4(lane) : 0u;
@@ -123,9 +132,10 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             if (valid) {
                 h = (v * 2654435761u) >> (32 - kHashBits);
                 const uint32_t c = table[h];
-                int q = (int)(((uint32_t)p & 0xFFFF0000u) | c);
-                if (q >= p) q -= 65536;
-                if (c != kEmpty) cand = q;
+                const int vp = p + kVirt;
+                int q = (int)(((uint32_t)vp & 0xFFFF0000u) | c);
+                if (q >= vp) q -= 65536;
+                if (c != kEmpty) cand = q - kVirt;               // < 0: inside the dictionary (kDict only)
             }
             const uint32_t same = __match_any_sync(FULL_MASK, h);
             const uint32_t lower = same & ((1u << lane) - 1u);
@@ -136,15 +146,21 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             // ---- (a2) every lane measures its own candidate: 1 byte backwards, 15 bytes forwards.
             // positions already covered by the previous match were inserted above but need no candidate;
             // candidate 0 is skipped so that the byte before the candidate always exists.
-            const bool want = valid && p >= anchor && cand >= 1 && (uint32_t)(p - cand) <= MAX_DISTANCE;
+            // dictionary candidates (cand < 0) must leave a byte before them inside the dictionary
+            const bool in_dict = kDict && cand < 0;
+            const int didx = cand + dsz;                              // index inside the dictionary when in_dict
+            const bool want = valid && p >= anchor && (uint32_t)(p - cand) <= MAX_DISTANCE &&
+                              (in_dict ? didx >= 1 : cand >= 1);
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
             uint32_t t = 0;
             if (want) {
-                const uint32_t ca = d16 + (uint32_t)cand - 1u;       // fetch starts at the byte before the candidate
+                // fetch starts at the byte before the candidate
+                const uint32_t ca = in_dict ? (dd16 + (uint32_t)didx - 1u) : (d16 + (uint32_t)cand - 1u);
+                const uint4* __restrict__ cb16 = in_dict ? dict16 : src16;
                 const uint32_t ci = ca >> 4;
                 t = ca & 15u;
-                r0 = src16[ci];
-                if (ci + 1 < end16) r1 = src16[ci + 1];
+                r0 = cb16[ci];
+                if (in_dict || ci + 1 < end16) r1 = cb16[ci + 1];    // the dictionary buffer carries 32 B of zeroed slack
             }
             // own bytes p-1 .. p+14 as four words, from the neighbours' registers
             uint32_t o0, o1, o2, o3;
@@ -177,11 +193,12 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
                 const uint32_t xs = z0 ? (z1 ? (z2 ? x3 : x2) : x1) : y0;
                 const int skip = z0 ? (z1 ? (z2 ? 11 : 7) : 3) : 0;
                 eqlen = skip + (__clz(__brev(xs)) >> 3);
-                const int room = match_end - p;
+                int room = match_end - p;
+                if (in_dict && dsz - didx < room) room = dsz - didx;   // a dictionary match stops at the dictionary's end
                 if (eqlen > room) eqlen = room;
             }
             const bool ok = want && eqlen >= MINMATCH;
-            const bool more = ok && eqlen == kProbe && p + kProbe < match_end;
+            const bool more = ok && eqlen == kProbe && p + kProbe < match_end && (!in_dict || didx + kProbe < dsz);
             const bool backok = kBack && ok && lane > 0 && backeq;
             const uint32_t bal = __ballot_sync(FULL_MASK, ok);
             // one-step lazy hint: the next position holds a strictly longer match
@@ -202,7 +219,13 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
                 if (pk & 4u) { f++; pk = __shfl_sync(FULL_MASK, pack, f) & ~2u; }
                 const uint32_t off = pk >> 16;
                 int mlen = (int)((pk >> 8) & 0xFFu);
-                if (pk & 1u) mlen += count_equal(src, base + f + kProbe, base + f - (int)off + kProbe, match_end, lane);
+                if (pk & 1u) {
+                    const int a0 = base + f + kProbe, c0 = a0 - (int)off;      // c0 < 0: candidate bytes are in the dictionary
+                    const bool cd = kDict && c0 < 0;
+                    const uint8_t* cp = cd ? dict + (c0 + dsz) : src + c0;
+                    const int lim = cd ? min(match_end - a0, -c0) : match_end - a0;
+                    mlen += count_equal(src + a0, cp, lim, lane);
+                }
                 const int s = ((pk & 2u) && f > pos) ? f - 1 : f;       // one byte backwards into the literals
                 mlen += f - s;
                 if (lane == s) { my_mlen = mlen; my_off = off; }
@@ -305,7 +328,7 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
     return op;
 }
 
-template <int kHashBits>
+template <int kHashBits, bool kDict>
 __global__ void __launch_bounds__(kEncodeWarps * 32, 6)
 lz4_compress_kernel(EncodeArgs a)
 {
@@ -322,7 +345,8 @@ lz4_compress_kernel(EncodeArgs a)
     uint8_t* payload = a.raw_blocks ? rec : rec + 4;
     uint16_t* table = reinterpret_cast<uint16_t*>(smem + warp * kTableBytes);
 
-    int c = encode_block<kHashBits>(src, n, payload, (int)a.dst_cap, table, lane);
+    int c = encode_block<kHashBits, kDict>(src, n, payload, (int)a.dst_cap, table, lane, a.dict, (int)a.dict_size,
+                                           a.dict_table);
 
     if (a.raw_blocks) {
         if (lane == 0) a.rec_len[b] = (uint32_t)c;      // 0 = does not fit (clz4.go:40-42)
@@ -347,14 +371,47 @@ lz4_compress_kernel(EncodeArgs a)
     if (lane == 0) a.rec_len[b] = total;
 }
 
+// Dictionary table: for every hash the LAST dictionary position holding it (what a block would have seen
+// had the dictionary been its own first bytes), as the low 16 bits of the virtual position.
+__global__ void __launch_bounds__(1024) dict_table_kernel(const uint8_t* __restrict__ dict, int dsz, int bits, uint16_t* __restrict__ table)
+{
+    extern __shared__ int best[];                      // highest position per hash, -1 = none
+    const int entries = 1 << bits;
+    for (int i = threadIdx.x; i < entries; i += blockDim.x) best[i] = -1;
+    __syncthreads();
+    for (int j = threadIdx.x; j + 4 <= dsz; j += blockDim.x) {
+        const uint32_t v = (uint32_t)dict[j] | ((uint32_t)dict[j + 1] << 8) | ((uint32_t)dict[j + 2] << 16) | ((uint32_t)dict[j + 3] << 24);
+        atomicMax(&best[(v * 2654435761u) >> (32 - bits)], j);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < entries; i += blockDim.x)
+        table[i] = best[i] < 0 ? (uint16_t)0xFFFF : (uint16_t)(65536 - dsz + best[i]);
+}
+
+cudaError_t launch_dict_build(const uint8_t* dict, uint32_t dict_size, int bits, uint16_t* table, cudaStream_t stream)
+{
+    dict_table_kernel<<<1, 1024, sizeof(int) << bits, stream>>>(dict, (int)dict_size, bits, table);
+    return cudaGetLastError();
+}
+
 static int g_hash_bits = 12;     // 8 KiB of table per warp: twice the resident warps of liblz4's 13 bits; the one-step
                                  // lazy parse more than pays the ratio back (profiles/r01_sweep.txt)
 
 template <int kBits>
 static cudaError_t set_smem_attr()
 {
-    return cudaFuncSetAttribute(lz4_compress_kernel<kBits>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(lz4_compress_kernel<kBits, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kEncodeWarps * (2 << kBits));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lz4_compress_kernel<kBits, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kEncodeWarps * (2 << kBits));
+}
+
+int compress_hash_bits(uint32_t dst_cap)
+{
+    // blocks above 64 KiB come in small numbers (64 per 256 MiB at 4 MiB): occupancy is not the limit there,
+    // so they get liblz4's 8192-entry table back
+    return (dst_cap > 65536u + 65536u / 255u + 16u) ? 13 : g_hash_bits;
 }
 
 cudaError_t configure_compress()
@@ -389,12 +446,12 @@ cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
 {
     if (a.nblk == 0) return cudaSuccess;
     dim3 grid((a.nblk + kEncodeWarps - 1) / kEncodeWarps), block(kEncodeWarps * 32);
-    // blocks above 64 KiB come in small numbers (64 per 256 MiB at 4 MiB): occupancy is not the limit there,
-    // so they get liblz4's 8192-entry table back
-    const int bits = (a.dst_cap > 65536u + 65536u / 255u + 16u) ? 13 : g_hash_bits;
-    if (bits == 11)      lz4_compress_kernel<11><<<grid, block, kEncodeWarps * (2 << 11), stream>>>(a);
-    else if (bits == 12) lz4_compress_kernel<12><<<grid, block, kEncodeWarps * (2 << 12), stream>>>(a);
-    else                        lz4_compress_kernel<13><<<grid, block, kEncodeWarps * (2 << 13), stream>>>(a);
+    const int bits = compress_hash_bits(a.dst_cap);
+    const size_t sm = (size_t)kEncodeWarps * (2u << bits);
+    const bool d = a.dict_size > 0;
+    if (bits == 11)      { if (d) lz4_compress_kernel<11, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<11, false><<<grid, block, sm, stream>>>(a); }
+    else if (bits == 12) { if (d) lz4_compress_kernel<12, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<12, false><<<grid, block, sm, stream>>>(a); }
+    else                 { if (d) lz4_compress_kernel<13, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<13, false><<<grid, block, sm, stream>>>(a); }
     return cudaGetLastError();
 }
 

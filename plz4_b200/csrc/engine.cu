@@ -149,9 +149,14 @@ inline uint32_t round_up16(uint32_t v) { return (v + 15u) & ~15u; }
 }  // namespace
 
 struct plz4cu_dict {
-    uint8_t* d_bytes = nullptr;     // device copy of the last <= 64 KiB
+    uint8_t* d_bytes = nullptr;     // device copy of the last <= 64 KiB (+ zeroed slack)
+    uint16_t* d_tables = nullptr;   // encoder tables for 11, 12 and 13 hash bits, back to back
     uint32_t size = 0;
     std::vector<uint8_t> h_bytes;
+    const uint16_t* table(int bits) const
+    {
+        return d_tables + (bits == 11 ? 0 : bits == 12 ? (1 << 11) : (1 << 11) + (1 << 12));
+    }
 };
 
 extern "C" {
@@ -217,12 +222,20 @@ plz4cu_dict_t* plz4cu_dict_create(const void* d, size_t n)
     dc->size = (uint32_t)n;
     dc->h_bytes.assign(b, b + n);
     if (n) {
-        // 16 bytes of slack so aligned-word reads near the end stay inside the allocation
-        cudaError_t e = cudaMalloc((void**)&dc->d_bytes, n + 16);
+        // 32 bytes of zeroed slack: the encoder fetches aligned 16-byte chunks around a candidate
+        cudaError_t e = cudaMalloc((void**)&dc->d_bytes, n + 48);
+        if (e == cudaSuccess) e = cudaMemset(dc->d_bytes, 0, n + 48);
         if (e == cudaSuccess) e = cudaMemcpy(dc->d_bytes, b, n, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dc->d_tables, sizeof(uint16_t) * ((1 << 11) + (1 << 12) + (1 << 13)));
+        for (int bits = 11; bits <= 13 && e == cudaSuccess; bits++) {
+            e = launch_dict_build(dc->d_bytes, dc->size, bits, const_cast<uint16_t*>(dc->table(bits)), nullptr);
+            g_launches++;
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
             fail(PLZ4CU_ERR_CUDA, "plz4cu_dict_create", e);
             if (dc->d_bytes) cudaFree(dc->d_bytes);
+            if (dc->d_tables) cudaFree(dc->d_tables);
             delete dc;
             return nullptr;
         }
@@ -233,6 +246,7 @@ void plz4cu_dict_destroy(plz4cu_dict_t* dc)
 {
     if (!dc) return;
     if (dc->d_bytes) cudaFree(dc->d_bytes);
+    if (dc->d_tables) cudaFree(dc->d_tables);
     delete dc;
 }
 
@@ -247,12 +261,12 @@ int plz4cu_compress_batch_device(plz4cu_stream_t stream, const void* src_base, c
     if (rec_stride & 15u) return fail(PLZ4CU_ERR_ARG, "compress_batch_device: rec_stride must be a multiple of 16");
     if ((reinterpret_cast<uintptr_t>(rec_base) & 15u) != 0) return fail(PLZ4CU_ERR_ARG, "compress_batch_device: rec_base must be 16-byte aligned");
     if ((uint64_t)rec_stride < (uint64_t)dst_cap + (raw_blocks ? 0 : PLZ4CU_REC_OVERHEAD)) return fail(PLZ4CU_ERR_ARG, "compress_batch_device: rec_stride too small for dst_cap");
-    if (dict && dict->size) return fail(PLZ4CU_ERR_ARG, "compress_batch_device: dictionary compression not available in this build");
     EncodeArgs a{};
     a.src_base = static_cast<const uint8_t*>(src_base);
     a.src_off = src_off; a.src_len = src_len; a.nblk = nblk; a.dst_cap = dst_cap;
     a.block_checksum = block_checksum; a.raw_blocks = raw_blocks;
     a.rec_base = static_cast<uint8_t*>(rec_base); a.rec_stride = rec_stride; a.rec_len = rec_len;
+    if (dict && dict->size) { a.dict = dict->d_bytes; a.dict_size = dict->size; a.dict_table = dict->table(compress_hash_bits(dst_cap)); }
     CU(launch_compress(a, static_cast<cudaStream_t>(stream)));
     g_launches++;
     return 0;
@@ -342,7 +356,6 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
     packed_off[0] = 0;
     if (nblk == 0) return 0;
     if (!src || !src_off || !src_len || !packed) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: null pointer");
-    if (dict && dict->size) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: dictionary compression not available in this build");
     Pipe* pp = pipe_for_current_device();
     if (!pp) return fail(PLZ4CU_ERR_NODEVICE, "no CUDA device");
     std::lock_guard<std::mutex> lk(pp->mu);
@@ -393,6 +406,7 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         a.src_len = reinterpret_cast<const uint32_t*>(L.off.as<uint64_t>() + cnt);
         a.nblk = cnt; a.dst_cap = dst_cap; a.block_checksum = block_checksum; a.raw_blocks = raw_blocks;
         a.rec_base = L.out.as<uint8_t>(); a.rec_stride = stride; a.rec_len = L.res.as<uint32_t>();
+        if (dict && dict->size) { a.dict = dict->d_bytes; a.dict_size = dict->size; a.dict_table = dict->table(compress_hash_bits(dst_cap)); }
         CU(launch_compress(a, L.st));
         CU(launch_pack(L.out.as<uint8_t>(), stride, L.res.as<uint32_t>(), cnt, L.packed.as<uint8_t>(), L.poff.as<uint64_t>(), L.st));
         g_launches += 3;

@@ -36,7 +36,7 @@ struct EncodeArgs {
     int raw_blocks;
     const uint8_t* dict;          // dictionary bytes (device) or nullptr
     uint32_t dict_size;
-    const uint16_t* dict_table;   // per-hash most recent dictionary position (device) or nullptr
+    const uint16_t* dict_table;   // the dictionary's table for compress_hash_bits(dst_cap) (device) or nullptr
     uint8_t* rec_base;
     uint32_t rec_stride;
     uint32_t* rec_len;
@@ -44,8 +44,9 @@ struct EncodeArgs {
 cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream);
 cudaError_t configure_compress();     // one-time function attributes (opt-in shared memory)
 
-// dictionary table build (hash -> last position), device side
-cudaError_t launch_dict_build(const uint8_t* dict, uint32_t dict_size, uint16_t* table, cudaStream_t stream);
+// dictionary table build (hash -> last position) for a given table size, device side
+cudaError_t launch_dict_build(const uint8_t* dict, uint32_t dict_size, int bits, uint16_t* table, cudaStream_t stream);
+int compress_hash_bits(uint32_t dst_cap);          // table size the encoder will use for this capacity
 
 cudaError_t launch_pack(const uint8_t* rec_base, uint32_t rec_stride, const uint32_t* rec_len, uint32_t nblk,
                         uint8_t* packed, uint64_t* packed_off, cudaStream_t stream);

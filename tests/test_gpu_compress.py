@@ -77,3 +77,47 @@ def test_logtext_ratio_vs_liblz4(gpu, codec):
     out, res = gpu.decompress_batch(packed, poff[:-1], bsz, verify_checksum=True)
     assert (res == bsz).all()
     assert out.reshape(-1).tobytes() == data
+
+
+def test_dictionary_compress_small_messages(gpu, port, codec):
+    """BASELINE configs[3] in miniature: 4 KiB payloads sharing a 64 KiB dictionary (raw block API)."""
+    from tests.datagen import logtext
+    corpus = logtext(1 << 20, seed=77)
+    d = corpus[:65536]
+    rng = np.random.default_rng(5)
+    starts = rng.integers(65536, len(corpus) - 4096, size=256)
+    msgs = [corpus[s: s + 4096] for s in starts] + [b"", b"x", d[-100:], d[1000:1200] * 3, make("random", 4096)]
+    gd, cd = gpu.Dict(d), codec.dict_create(d)
+    buf, lens = b"".join(msgs), [len(m) for m in msgs]
+    off = np.cumsum([0] + lens)[:-1]
+    packed, poff = gpu.compress_batch(buf, off, lens, gpu.compress_block_bound(4096), raw_blocks=True, dict=gd)
+    tot_gpu = tot_ref = tot_nodict = 0
+    for i, m in enumerate(msgs):
+        c = packed[int(poff[i]): int(poff[i + 1])].tobytes()
+        r, data = cd.decompress(c, len(m))               # the reference decoder with the same dictionary
+        assert r == len(m) and data == m, i
+        tot_gpu += len(c)
+        tot_ref += len(cd.compress(m))
+        tot_nodict += len(codec.compress(m))
+    print(f"dict: gpu {tot_gpu} liblz4+dict {tot_ref} liblz4 no dict {tot_nodict}")
+    assert tot_gpu <= tot_ref * TOLERANCE
+    assert tot_gpu < tot_nodict * 0.92                   # the dictionary is really used (wr_test.go:471-625)
+    # and back through the GPU decoder with the dictionary
+    out, res = gpu.decompress_batch(packed, poff[:-1], 4096, raw_len=np.diff(poff).astype(np.uint32), dict=gd)
+    for i, m in enumerate(msgs):
+        assert res[i] == len(m) and out[i, : len(m)].tobytes() == m
+
+
+@pytest.mark.parametrize("dn", [0, 3, 4, 100, 5000, 65535, 65536, 70000])
+def test_dictionary_sizes_and_block_api(gpu, codec, dn):
+    d = make("words", dn, seed=9)
+    gd, cd = gpu.Dict(d), codec.dict_create(d)
+    for n in [0, 1, 13, 300, 4096, 65536, 100000]:
+        for kind in ["words", "log"]:
+            m = make(kind, n, seed=9)
+            if dn >= 64 and n >= 64:
+                m = (d[-50:] + m)[:n]                    # begins with the dictionary's tail
+            c = gpu.compress_block(m, dict=gd)
+            r, data = cd.decompress(c, len(m))
+            assert r == len(m) and data == m, (dn, n, kind)
+            assert gpu.decompress_block(c, dst_cap=len(m), dict=gd) == m
