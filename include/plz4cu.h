@@ -169,6 +169,118 @@ PLZ4CU_API int plz4cu_decompress_safe_dict(const plz4cu_dict_t* dict, const void
 PLZ4CU_API int plz4cu_xxh32_batch_device(plz4cu_stream_t stream, const void* base, const uint64_t* off,
                               const uint32_t* len, uint32_t nblk, uint32_t* out);
 
+
+/* ---------------------------------------------------------------- frame streams (host side of the path)
+ *
+ * C mirror of plz4.NewWriter / plz4.NewReader (plz4_writer.go:14-53, plz4_reader.go:12-33) with the
+ * option set of plz4_opts.go:70-255.  The frame header / descriptor / trailer logic, block slicing,
+ * Flush barrier, progress callbacks, WithReadOffset, skip frames, frame concatenation, content checksum
+ * (serial xxh32 on a host core) and the sticky error state live here on the host; every block goes
+ * through the batched GPU engine above.  What replaces what:
+ *   writer : internal/pkg/sync/writer.go + internal/pkg/async/writer.go (batcher instead of compressLoop)
+ *   reader : internal/pkg/rdr/rdr.go + internal/pkg/blk/frame.go:54-139 + internal/pkg/async/reader.go
+ *   header : internal/pkg/header/{write,read,skip}.go, descriptor/*.go, trailer/trailer.go
+ * Not supported by this engine (reported as PLZ4CU_Z_UNSUPPORTED, never silently degraded):
+ *   levels 2-12 (lz4hc.c) and linked blocks (compress/linked.go) — the reference runs those on CPU cores.
+ *
+ * I/O goes through callbacks so any io.Reader / io.Writer can sit behind them:
+ *   write: return bytes written (== n) or a negative value to signal an I/O error
+ *   read : return bytes read (short reads allowed), 0 at end of stream, negative on I/O error
+ *   seek : optional (may be NULL): skip `delta` bytes forward; return 0, or negative if it cannot seek
+ */
+typedef int64_t (*plz4cu_write_fn)(void* ctx, const void* data, size_t n);
+typedef int64_t (*plz4cu_read_fn)(void* ctx, void* buf, size_t n);
+typedef int     (*plz4cu_seek_fn)(void* ctx, int64_t delta);
+/* opts.ProgressFuncT (plz4_opts.go:113-124): (src_block_offset, dst_block_offset) at every block boundary. */
+typedef void    (*plz4cu_progress_fn)(void* ctx, int64_t src_off, int64_t dst_off);
+/* opts.SkipCallbackT: called with a skippable frame's payload (already read: at most sz bytes). */
+typedef int     (*plz4cu_skip_fn)(void* ctx, uint8_t nibble, const void* payload, uint32_t sz);
+/* opts.DictCallbackT: may return a dictionary for the dictionary id found in a frame header. */
+typedef int     (*plz4cu_dict_fn)(void* ctx, uint32_t dict_id, const void** dict, size_t* dict_len);
+
+typedef struct plz4cu_opts {
+    int32_t  level;              /* WithLevel: only 1 is implemented by this engine                       */
+    int32_t  n_parallel;         /* WithParallel: 0 = one block per engine call; != 0 = batched            */
+    int32_t  pending_size;       /* WithPendingSize: bytes of blocks batched per engine call (-1/0 = auto) */
+    int32_t  block_size_idx;     /* WithBlockSize: 4..7 (64 KiB, 256 KiB, 1 MiB, 4 MiB)                    */
+    int32_t  block_checksum;     /* WithBlockChecksum                                                      */
+    int32_t  content_checksum;   /* WithContentChecksum                                                    */
+    int32_t  block_linked;       /* WithBlockLinked: unsupported (PLZ4CU_Z_UNSUPPORTED)                    */
+    int32_t  has_content_size;   /* WithContentSize                                                        */
+    uint64_t content_size;
+    int32_t  has_dict_id;        /* WithDictionaryId                                                       */
+    uint32_t dict_id;
+    const void* dict;            /* WithDictionary (last 64 KiB used)                                      */
+    size_t   dict_len;
+    int64_t  read_offset;        /* WithReadOffset                                                         */
+    int32_t  content_size_check; /* WithContentSizeCheck                                                   */
+    int32_t  reserved0;
+    plz4cu_progress_fn progress; void* progress_ctx;   /* WithProgress      */
+    plz4cu_skip_fn     skip_cb;  void* skip_ctx;       /* WithSkipCallback  */
+    plz4cu_dict_fn     dict_cb;  void* dict_ctx;       /* WithDictCallback  */
+} plz4cu_opts_t;
+
+/* parseOpts defaults (plz4_opts.go:238-255): level 1, parallel 1, 4 MiB blocks, content checksum on. */
+PLZ4CU_API void plz4cu_opts_default(plz4cu_opts_t* o);
+
+/* Stream error codes: the reference's sentinel errors (internal/pkg/zerr/zerr.go:11-41). */
+#define PLZ4CU_Z_CLOSED               -101
+#define PLZ4CU_Z_HEADER_HASH          -102   /* corrupted */
+#define PLZ4CU_Z_BLOCK_HASH           -103   /* corrupted */
+#define PLZ4CU_Z_CONTENT_HASH         -104   /* corrupted */
+#define PLZ4CU_Z_HEADER_READ          -105
+#define PLZ4CU_Z_HEADER_WRITE         -106
+#define PLZ4CU_Z_MAGIC                -107   /* corrupted */
+#define PLZ4CU_Z_VERSION              -108
+#define PLZ4CU_Z_BLOCK_SIZE_READ      -109
+#define PLZ4CU_Z_BLOCK_READ           -110
+#define PLZ4CU_Z_BLOCK_SIZE_OVERFLOW  -111   /* corrupted */
+#define PLZ4CU_Z_DECOMPRESS           -112   /* corrupted */
+#define PLZ4CU_Z_RESERVE_BIT          -113   /* corrupted */
+#define PLZ4CU_Z_BLOCK_DESCRIPTOR     -114   /* corrupted */
+#define PLZ4CU_Z_CONTENT_HASH_READ    -115
+#define PLZ4CU_Z_CONTENT_SIZE         -116   /* corrupted */
+#define PLZ4CU_Z_READ_OFFSET          -117
+#define PLZ4CU_Z_READ_OFFSET_LINKED   -118
+#define PLZ4CU_Z_SKIP                 -119
+#define PLZ4CU_Z_NIBBLE               -120
+#define PLZ4CU_Z_UNSUPPORTED          -121
+#define PLZ4CU_Z_WRITE                -122   /* the write callback failed (the Go code returns the io error itself) */
+#define PLZ4CU_Z_ENGINE               -123   /* CUDA / engine failure: see plz4cu_last_error() */
+/* plz4.Lz4Corrupted (plz4_err.go:43-45). */
+PLZ4CU_API int plz4cu_err_corrupted(int code);
+PLZ4CU_API const char* plz4cu_strerror(int code);
+
+typedef struct plz4cu_writer plz4cu_writer_t;
+typedef struct plz4cu_reader plz4cu_reader_t;
+
+/* plz4.NewWriter (plz4_writer.go:40-53). */
+PLZ4CU_API plz4cu_writer_t* plz4cu_writer_new(plz4cu_write_fn wr, void* wr_ctx, const plz4cu_opts_t* opts);
+/* Writer.Write: bytes consumed (== n) or a negative PLZ4CU_Z_* code. */
+PLZ4CU_API int64_t plz4cu_writer_write(plz4cu_writer_t* w, const void* src, size_t n);
+/* Writer.ReadFrom: bytes consumed from `rd` until it reports end of stream, or a negative code. */
+PLZ4CU_API int64_t plz4cu_writer_read_from(plz4cu_writer_t* w, plz4cu_read_fn rd, void* rd_ctx);
+/* Writer.Flush: synchronous barrier, emits the pending partial block (async/writer.go:109-133). */
+PLZ4CU_API int plz4cu_writer_flush(plz4cu_writer_t* w);
+/* Writer.Close: flush + EndMark (+ content checksum); 0 or a negative code (async/writer.go:135-191). */
+PLZ4CU_API int plz4cu_writer_close(plz4cu_writer_t* w);
+PLZ4CU_API void plz4cu_writer_free(plz4cu_writer_t* w);
+
+/* plz4.NewReader (plz4_reader.go:28-33).  Lazy: nothing is read until the first Read / WriteTo. */
+PLZ4CU_API plz4cu_reader_t* plz4cu_reader_new(plz4cu_read_fn rd, plz4cu_seek_fn seek, void* rd_ctx, const plz4cu_opts_t* opts);
+/* Reader.Read: > 0 bytes produced, 0 = end of stream (io.EOF), negative = PLZ4CU_Z_* (rdr/rdr.go:39-87). */
+PLZ4CU_API int64_t plz4cu_reader_read(plz4cu_reader_t* r, void* dst, size_t n);
+/* Reader.WriteTo: total bytes written, or a negative code (rdr/rdr.go:139-174). */
+PLZ4CU_API int64_t plz4cu_reader_write_to(plz4cu_reader_t* r, plz4cu_write_fn wr, void* wr_ctx);
+PLZ4CU_API int plz4cu_reader_close(plz4cu_reader_t* r);
+PLZ4CU_API void plz4cu_reader_free(plz4cu_reader_t* r);
+
+/* plz4.WriteSkipFrameHeader (plz4_writer.go:56-62, header/skip.go:18-34): 8 bytes. */
+PLZ4CU_API int plz4cu_write_skip_frame_header(plz4cu_write_fn wr, void* wr_ctx, uint8_t nibble, uint32_t sz);
+
+/* xxh32.ChecksumZero of a host buffer, computed on the host (header HC byte, content checksum). */
+PLZ4CU_API uint32_t plz4cu_xxh32_host(const void* p, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

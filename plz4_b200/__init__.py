@@ -8,3 +8,4 @@ from .api import (  # noqa: F401
     Dict, Lz4Error, Plz4cuError, compress_batch, compress_block, compress_block_bound,
     decompress_batch, decompress_block, init, lz4_corrupted,
 )
+from .stream import NewReader, NewWriter, Reader, StreamError, Writer, write_skip_frame_header  # noqa: F401,E402

@@ -50,7 +50,46 @@ SIGNATURES = {
     "plz4cu_decompress_safe": (_int, [_vp, _int, _vp, _int]),
     "plz4cu_decompress_safe_dict": (_int, [_vp, _vp, _int, _vp, _int]),
     "plz4cu_xxh32_batch_device": (_int, [_vp, _vp, _vp, _vp, _u32, _vp]),
+    # frame streams
+    "plz4cu_opts_default": (None, [_vp]),
+    "plz4cu_err_corrupted": (_int, [_int]),
+    "plz4cu_strerror": (C.c_char_p, [_int]),
+    "plz4cu_writer_new": (_vp, [_vp, _vp, _vp]),
+    "plz4cu_writer_write": (C.c_int64, [_vp, _vp, _sz]),
+    "plz4cu_writer_read_from": (C.c_int64, [_vp, _vp, _vp]),
+    "plz4cu_writer_flush": (_int, [_vp]),
+    "plz4cu_writer_close": (_int, [_vp]),
+    "plz4cu_writer_free": (None, [_vp]),
+    "plz4cu_reader_new": (_vp, [_vp, _vp, _vp, _vp]),
+    "plz4cu_reader_read": (C.c_int64, [_vp, _vp, _sz]),
+    "plz4cu_reader_write_to": (C.c_int64, [_vp, _vp, _vp]),
+    "plz4cu_reader_close": (_int, [_vp]),
+    "plz4cu_reader_free": (None, [_vp]),
+    "plz4cu_write_skip_frame_header": (_int, [_vp, _vp, C.c_uint8, _u32]),
+    "plz4cu_xxh32_host": (_u32, [_vp, _sz]),
 }
+
+WRITE_FN = C.CFUNCTYPE(C.c_int64, _vp, _vp, _sz)
+READ_FN = C.CFUNCTYPE(C.c_int64, _vp, _vp, _sz)
+SEEK_FN = C.CFUNCTYPE(_int, _vp, C.c_int64)
+PROGRESS_FN = C.CFUNCTYPE(None, _vp, C.c_int64, C.c_int64)
+SKIP_FN = C.CFUNCTYPE(_int, _vp, C.c_uint8, _vp, _u32)
+DICT_FN = C.CFUNCTYPE(_int, _vp, _u32, C.POINTER(_vp), C.POINTER(_sz))
+
+
+class Opts(C.Structure):
+    """plz4cu_opts_t (include/plz4cu.h)."""
+    _fields_ = [
+        ("level", C.c_int32), ("n_parallel", C.c_int32), ("pending_size", C.c_int32), ("block_size_idx", C.c_int32),
+        ("block_checksum", C.c_int32), ("content_checksum", C.c_int32), ("block_linked", C.c_int32),
+        ("has_content_size", C.c_int32), ("content_size", C.c_uint64),
+        ("has_dict_id", C.c_int32), ("dict_id", C.c_uint32),
+        ("dict", _vp), ("dict_len", _sz),
+        ("read_offset", C.c_int64), ("content_size_check", C.c_int32), ("reserved0", C.c_int32),
+        ("progress", PROGRESS_FN), ("progress_ctx", _vp),
+        ("skip_cb", SKIP_FN), ("skip_ctx", _vp),
+        ("dict_cb", DICT_FN), ("dict_ctx", _vp),
+    ]
 
 
 def header_symbols() -> list[str]:
