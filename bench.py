@@ -341,7 +341,7 @@ def run_gpu(args) -> None:
                        "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                        "bytes_per_gpu": int(e2e["bytes"]), "steps": e2e["steps"],
                        "api": "plz4cu_compress_batch_host + plz4cu_decompress_batch_host, pinned host buffers"}
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:       # reported on rank 0 at N=1 only
         try:
             r = cpu_reference(args.cpu_sample_mib << 20, 3, 1)
             line["cpu_baseline"] = {k: (round(r[k], 4) if isinstance(r[k], float) else r[k])
