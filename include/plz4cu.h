@@ -5,6 +5,10 @@
  * (and the per-block fan-out in internal/pkg/async) binds to.  Plain pointers and sizes only.
  * Reference interface each entry point replaces is cited as file:line relative to the plz4 tree.
  *
+ * Memory contract: the kernels fetch whole aligned 4- and 16-byte words.  Device input buffers (sources, records,
+ * dictionaries) must therefore be readable up to the next 16-byte boundary after their last byte — true for every
+ * CUDA allocation; nothing past that boundary is touched (profiles/r01_sanitizer.txt).  Outputs are written exactly.
+ *
  * Block record layout (identical to blk.CompressToBlk, internal/pkg/blk/blk.go:87-106):
  *     [ LE32 size | bit31 = stored uncompressed ][ payload ][ LE32 xxh32(payload) if block checksum ]
  *
