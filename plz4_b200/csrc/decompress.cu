@@ -9,116 +9,276 @@
 // Accept/reject behaviour and the negative return code follow liblz4's decode_full_block state
 // machine exactly (derivation: DESIGN.md "decoder state machine").
 //
-// Work split inside the warp: the sequence parse is warp-uniform (every lane reads the same token /
-// offset bytes, which the LSU serves as one broadcast), the byte movement is lane-parallel.  A match
-// never needs lane-to-lane ordering inside itself because byte k of a match with offset `off` is
-// out[op - off + (k mod off)] — always a byte that was final before the match started — so the only
-// synchronisation is one __syncwarp() before a match reads what earlier sequences wrote.
+// How the warp works.  A sequence-at-a-time decoder leaves most lanes idle (an average sequence on
+// log text is ~14 output bytes) and pays the whole parse per sequence.  So the warp decodes in
+// BATCHES of up to 32 sequences:
+//   1. parse: the token chain is walked once (warp-uniform, broadcast byte loads); lane k keeps the
+//      fields of sequence k.  Only "shortcut" sequences (lz4.c:2100-2108: literal nibble < 15, >= 17
+//      input bytes left) enter a batch; anything else ends the batch and is handled by the
+//      sequence-at-a-time path below, which is the literal statement of the state machine.
+//   2. scan: output positions of all sequences by a warp prefix sum; the capacity / offset checks
+//      that depend on the output position are evaluated for all 32 sequences at once.
+//   3. copy: the batch's output range is produced 32 bytes at a time, one byte per lane.  A lane finds
+//      the sequence owning its byte (a shared-memory bitmap of sequence starts + popc), computes where the byte comes
+//      from — the compressed stream (literal), the dictionary, or earlier output (match) — and only
+//      bytes whose source lies inside the same 32-byte chunk need lane-to-lane forwarding (pointer
+//      doubling over shuffles).  All loads of a chunk are independent, so match sources that miss
+//      L1/L2 overlap instead of serialising.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace plz4 {
 
-struct DecodeOut { int32_t ret; };
+// ---------------------------------------------------------------- one sequence at a time (state machine, literal form)
+
+enum : int { kStepMore = 0, kStepDone = 1 };
+
+// Decodes exactly one sequence starting at ip/op.  Returns kStepMore (ip/op advanced) or kStepDone (ret set).
+template <bool kDict>
+__device__ __noinline__ int decode_one(const uint8_t* __restrict__ src, int n, uint8_t* dst, int cap,
+                                       const uint8_t* __restrict__ dict, int dsz, int lane, int& ip, int& op, int32_t& ret)
+{
+    const bool check_offset = dsz < 65536;
+    const uint32_t tok = src[ip++];
+    int len = (int)(tok >> 4);
+    int mlen;
+    uint32_t off;
+
+    if (len != 15 && ip < n - 16 && op <= cap - 32) {
+        // "shortcut" sequence: cannot be the last one, no end-of-block checks (lz4.c:2100-2108,2250-2256)
+        if (lane < len) dst[op + lane] = src[ip + lane];
+        op += len; ip += len;
+        mlen = (int)(tok & 15);
+        off = load_u16le(src + ip); ip += 2;
+        if (mlen != 15 && off >= 8 && (int)off <= op) {
+            mlen += MINMATCH;                      // <= 18 bytes: one round
+            __syncwarp();
+            if (lane < mlen) {
+                int k = ((int)off >= mlen) ? lane : (lane % (int)off);
+                dst[op + lane] = dst[op - (int)off + k];
+            }
+            op += mlen;
+            return kStepMore;
+        }
+    } else {
+        if (len == 15) {
+            // read_variable_length(ip, iend-15, initial_check) lz4.c:1978-2014
+            if (ip >= n - 15) { ret = -ip - 1; return kStepDone; }
+            uint32_t s;
+            do {
+                s = src[ip++];
+                len += (int)s;
+                if (ip > n - 15) { ret = -ip - 1; return kStepDone; }
+            } while (s == 255);
+        }
+        if (op + len > cap - MFLIMIT || ip + len > n - (2 + 1 + LASTLITERALS)) {
+            // must be the last sequence: consume the input exactly, fit the output (lz4.c:2297-2330)
+            if (ip + len != n || op + len > cap) { ret = -ip - 1; return kStepDone; }
+            warp_copy(dst + op, src + ip, (uint32_t)len, lane);
+            ret = op + len;
+            return kStepDone;
+        }
+        warp_copy(dst + op, src + ip, (uint32_t)len, lane);
+        op += len; ip += len;
+        off = load_u16le(src + ip); ip += 2;
+        mlen = (int)(tok & 15);
+    }
+
+    // general match (lz4.c:2342-2430)
+    if (mlen == 15) {
+        uint32_t s;
+        do {
+            s = src[ip++];
+            mlen += (int)s;
+            if (ip > n - LASTLITERALS + 1) { ret = -ip - 1; return kStepDone; }
+        } while (s == 255);
+    }
+    mlen += MINMATCH;
+    if (check_offset && op - (int)off + dsz < 0) { ret = -ip - 1; return kStepDone; }
+    if (off == 0) { ret = -ip - 1; return kStepDone; }        // stated divergence: liblz4 would replay garbage
+    if (op + mlen > cap - LASTLITERALS) { ret = -ip - 1; return kStepDone; }
+
+    __syncwarp();
+    {
+        // virtual history = dict ++ out; byte k comes from v = op - off + (k mod off) (v < 0: dictionary)
+        const int vbase = op - (int)off;
+        if ((int)off >= mlen) {
+            if (!kDict || vbase >= 0) {
+                const uint8_t* s = dst + vbase;
+                for (int k = lane; k < mlen; k += 32) dst[op + k] = s[k];
+            } else {
+                for (int k = lane; k < mlen; k += 32) {
+                    int v = vbase + k;
+                    dst[op + k] = (v < 0) ? dict[dsz + v] : dst[v];
+                }
+            }
+        } else {
+            // overlapping: periodic with period off
+            int r = lane % (int)off;
+            const int step = 32 % (int)off;
+            for (int k = lane; k < mlen; k += 32) {
+                int v = vbase + r;
+                uint8_t b;
+                if (kDict && v < 0) b = dict[dsz + v]; else b = dst[v];
+                dst[op + k] = b;
+                r += step; if (r >= (int)off) r -= (int)off;
+            }
+        }
+    }
+    op += mlen;
+    __syncwarp();
+    return kStepMore;
+}
+
+// ---------------------------------------------------------------- batched decode
 
 template <bool kDict>
 __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src, int n,
                                                 uint8_t* dst, int cap,
-                                                const uint8_t* __restrict__ dict, int dsz, int lane)
+                                                const uint8_t* __restrict__ dict, int dsz, int lane, uint32_t* bitmap)
 {
+    constexpr int kBatchBytes = 1024;               // output bytes one batch may span (32 bitmap words)
     if (cap == 0) return (n == 1 && src[0] == 0) ? 0 : -1;
     if (n == 0) return -1;
 
     int ip = 0, op = 0;
     const bool check_offset = dsz < 65536;
+    // word-aligned view of the compressed stream: byte q of src is byte (d4 + q) of src4
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+    const uint32_t* __restrict__ src4 = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+    const uint32_t d4 = (uint32_t)sa & 3u;
+    const uint32_t last4 = (d4 + (uint32_t)n - 1u) >> 2;         // last word holding a valid byte
 
     for (;;) {
-        const uint32_t tok = src[ip++];
-        int len = (int)(tok >> 4);
-        int mlen;
-        uint32_t off;
+        // ---- 1. parse up to 32 shortcut sequences; lane k latches sequence k.
+        // The next 128 compressed bytes sit in registers (one word per lane).  Every lane first computes, for
+        // each of its own 4 bytes, how long a sequence header starting there would be (token + literals +
+        // offset [+ one length byte]); walking the token chain is then one shuffle per sequence instead of three
+        // dependent loads.  Headers that do not fit the simple shape (literal nibble 15, more than one length
+        // byte, too close to the end of the input) end the batch and go through decode_one.
+        int nseq = 0;
+        int my_lit = 0, my_litpos = 0, my_mlen = 0, my_ipn = 0;
+        uint32_t my_off = 0;
+        bool my_simple = false;                     // second shortcut stage applies on the input side (nibble != 15, offset >= 8)
+        {
+            const uint32_t a0 = d4 + (uint32_t)ip;              // byte address of ip relative to src4
+            const uint32_t w0 = a0 >> 2;                        // first window word
+            const uint32_t widx = w0 + (uint32_t)lane;
+            const uint32_t w = (widx <= last4) ? src4[widx] : 0u;
+            // header length if a token started at each of my 4 bytes (3 + literals, + 1 if the match nibble is 15)
+            uint32_t dpack = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t tok = (w >> (8 * i)) & 0xFFu;
+                const uint32_t dl = 3u + (tok >> 4) + ((tok & 15u) == 15u ? 1u : 0u);
+                dpack |= dl << (8 * i);
+            }
+            // walk the chain: qb = byte offset inside the window
+            uint32_t qb = a0 & 3u;
+            uint32_t myq = 0;
+            while (nseq < 32 && qb <= 128u - 20u) {
+                if (lane == nseq) myq = qb;
+                const uint32_t dl = (__shfl_sync(FULL_MASK, dpack, qb >> 2) >> ((qb & 3u) * 8u)) & 0xFFu;
+                qb += dl;
+                nseq++;
+            }
+            // each lane decodes its own header from the window
+            auto wbyte = [&](uint32_t bo) -> uint32_t {        // byte at window offset bo (< 128)
+                return (__shfl_sync(FULL_MASK, w, bo >> 2) >> ((bo & 3u) * 8u)) & 0xFFu;
+            };
+            const uint32_t tok = wbyte(myq);
+            const uint32_t L = tok >> 4, M = tok & 15u;
+            const uint32_t ob = myq + 1u + (L < 15u ? L : 0u);  // window offset of the match offset
+            const uint32_t off = wbyte(ob) | (wbyte(ob + 1u) << 8);
+            const uint32_t ext = wbyte(ob + 2u);
+            const int pos = ip + (int)(myq - (a0 & 3u));        // position of my token in src
+            const int ip1 = pos + 1;
+            const int ipn = ip1 + (int)L + 2 + (M == 15u ? 1 : 0);
+            const bool good = lane < nseq && L != 15u && ip1 < n - 16 &&
+                              (M != 15u || (ext != 255u && ipn <= n - LASTLITERALS + 1));
+            const uint32_t badseq = __ballot_sync(FULL_MASK, lane < nseq && !good);
+            if (badseq) nseq = __ffs(badseq) - 1;               // decode_one takes the first one that does not fit
+            my_lit = (int)L; my_litpos = ip1; my_off = off;
+            my_mlen = (int)M + MINMATCH + (M == 15u ? (int)ext : 0);
+            my_ipn = ipn;
+            my_simple = (M != 15u) && off >= 8u;
+        }
 
-        if (len != 15 && ip < n - 16 && op <= cap - 32) {
-            // "shortcut" sequence: cannot be the last one, no end-of-block checks (lz4.c:2100-2108,2250-2256)
-            if (lane < len) dst[op + lane] = src[ip + lane];
-            op += len; ip += len;
-            mlen = (int)(tok & 15);
-            off = load_u16le(src + ip); ip += 2;
-            if (mlen != 15 && off >= 8 && (int)off <= op) {
-                mlen += MINMATCH;                      // <= 18 bytes: one round
+        if (nseq > 0) {
+            // ---- 2. output positions (prefix sum) and the checks that depend on them
+            const int span = (lane < nseq) ? my_lit + my_mlen : 0;
+            int incl = span;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(FULL_MASK, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const int o = op + incl - span;                     // where my literals start
+            const int m = o + my_lit;                           // where my match starts
+            // a sequence is a shortcut only while op <= cap-32 (output side); the start bitmap below covers 1024 output
+            // bytes: cut the batch at the first sequence that breaks either limit
+            const uint32_t late = __ballot_sync(FULL_MASK, lane < nseq && (o > cap - 32 || o + span - op > kBatchBytes));
+            if (late) nseq = __ffs(late) - 1;
+            if (nseq > 0) {
+                const bool mine = lane < nseq;
+                const bool stage2 = my_simple && (int)my_off <= m;
+                const bool bad = mine && !stage2 &&
+                                 ((check_offset && m - (int)my_off + dsz < 0) || my_off == 0 || m + my_mlen > cap - LASTLITERALS);
+                const uint32_t badmask = __ballot_sync(FULL_MASK, bad);
+                if (badmask) return -__shfl_sync(FULL_MASK, my_ipn, __ffs(badmask) - 1) - 1;
+
+                // ---- 3. copy: 32 output bytes per step, one per lane
+                const int out0 = op;
+                const int out1 = __shfl_sync(FULL_MASK, o + span, nseq - 1);
+                const int orel = mine ? o - out0 : 0x7FFFFFF;                 // sequences outside the batch start "never"
+                // bitmap of sequence starts over the batch's output range: lane j ends up with bits out0+32j .. out0+32j+31
+                bitmap[lane] = 0;
                 __syncwarp();
-                if (lane < mlen) {
-                    int k = ((int)off >= mlen) ? lane : (lane % (int)off);
-                    dst[op + lane] = dst[op - (int)off + k];
+                if (mine) atomicOr(&bitmap[orel >> 5], 1u << (orel & 31));
+                __syncwarp();
+                const uint32_t my_bits = bitmap[lane];
+                // everything a byte needs to know about its sequence, in two words
+                const uint32_t packA = (uint32_t)(orel & 0x7FF) | ((uint32_t)my_lit << 11) | (my_off << 15);
+                uint8_t* dx = dst + out0 + lane;
+                int j = 0;
+                for (int c = 0; c < out1 - out0; c += 32, j++, dx += 32) {
+                    const int xr = c + lane;                                                        // byte position relative to out0
+                    // owner of the byte = last sequence starting at or before it
+                    const uint32_t sbits = __shfl_sync(FULL_MASK, my_bits, j);
+                    const int k = __popc(__ballot_sync(FULL_MASK, orel < c)) - 1 + __popc(sbits & ((2u << lane) - 1u));
+                    const uint32_t ka = __shfl_sync(FULL_MASK, packA, k);
+                    const int kp = __shfl_sync(FULL_MASK, my_litpos, k);
+                    const bool live = xr < out1 - out0;
+                    const int d = xr - (int)(ka & 0x7FFu);                                          // byte index inside the sequence
+                    const bool is_lit = d < (int)((ka >> 11) & 15u);
+                    const int sr = xr - (int)(ka >> 15);                                            // match source, relative to out0
+                    const bool fwd = live && !is_lit && sr >= c;                                    // source inside this chunk
+                    uint32_t val = 0;
+                    if (live && !fwd) {
+                        const int s = out0 + sr;
+                        const uint8_t* from = is_lit ? src + kp + d : ((kDict && s < 0) ? dict + dsz + s : dst + s);
+                        val = *from;
+                    }
+                    if (__any_sync(FULL_MASK, fwd)) {
+                        // forward values along in-chunk chains: root = the lane whose loaded value this byte finally equals
+                        int root = fwd ? (sr - c) : lane;
+#pragma unroll
+                        for (int it = 0; it < 5; it++) root = __shfl_sync(FULL_MASK, root, root);
+                        val = __shfl_sync(FULL_MASK, val, root);
+                    }
+                    if (live) *dx = (uint8_t)val;
+                    __syncwarp();
                 }
-                op += mlen;
+                ip = __shfl_sync(FULL_MASK, my_ipn, nseq - 1);
+                op = out1;
                 continue;
             }
-        } else {
-            if (len == 15) {
-                // read_variable_length(ip, iend-15, initial_check) lz4.c:1978-2014
-                if (ip >= n - 15) return -ip - 1;
-                uint32_t s;
-                do {
-                    s = src[ip++];
-                    len += (int)s;
-                    if (ip > n - 15) return -ip - 1;
-                } while (s == 255);
-            }
-            if (op + len > cap - MFLIMIT || ip + len > n - (2 + 1 + LASTLITERALS)) {
-                // must be the last sequence: consume the input exactly, fit the output (lz4.c:2297-2330)
-                if (ip + len != n || op + len > cap) return -ip - 1;
-                warp_copy(dst + op, src + ip, (uint32_t)len, lane);
-                return op + len;
-            }
-            warp_copy(dst + op, src + ip, (uint32_t)len, lane);
-            op += len; ip += len;
-            off = load_u16le(src + ip); ip += 2;
-            mlen = (int)(tok & 15);
         }
 
-        // general match (lz4.c:2342-2430)
-        if (mlen == 15) {
-            uint32_t s;
-            do {
-                s = src[ip++];
-                mlen += (int)s;
-                if (ip > n - LASTLITERALS + 1) return -ip - 1;
-            } while (s == 255);
-        }
-        mlen += MINMATCH;
-        if (check_offset && op - (int)off + dsz < 0) return -ip - 1;
-        if (off == 0) return -ip - 1;        // stated divergence: liblz4 would replay garbage
-        if (op + mlen > cap - LASTLITERALS) return -ip - 1;
-
-        __syncwarp();
-        {
-            // virtual history = dict ++ out; byte k comes from v = op - off + (k mod off) (v < 0: dictionary)
-            const int vbase = op - (int)off;
-            if ((int)off >= mlen) {
-                if (!kDict || vbase >= 0) {
-                    const uint8_t* s = dst + vbase;
-                    for (int k = lane; k < mlen; k += 32) dst[op + k] = s[k];
-                } else {
-                    for (int k = lane; k < mlen; k += 32) {
-                        int v = vbase + k;
-                        dst[op + k] = (v < 0) ? dict[dsz + v] : dst[v];
-                    }
-                }
-            } else {
-                // overlapping: periodic with period off
-                int r = lane % (int)off;
-                const int step = 32 % (int)off;
-                for (int k = lane; k < mlen; k += 32) {
-                    int v = vbase + r;
-                    uint8_t b;
-                    if (kDict && v < 0) b = dict[dsz + v]; else b = dst[v];
-                    dst[op + k] = b;
-                    r += step; if (r >= (int)off) r -= (int)off;
-                }
-            }
-        }
-        op += mlen;
+        // ---- anything that is not a shortcut sequence: one sequence through the literal state machine
+        int32_t ret = 0;
+        if (decode_one<kDict>(src, n, dst, cap, dict, dsz, lane, ip, op, ret) == kStepDone) return ret;
+        __syncwarp();                                   // its stores may be the next batch's match sources
     }
 }
 
@@ -126,6 +286,7 @@ template <bool kDict>
 __global__ void __launch_bounds__(kDecodeThreads)
 lz4_decompress_kernel(DecodeArgs a)
 {
+    __shared__ uint32_t s_bitmap[kDecodeThreads / 32][32];
     const int lane = lane_id();
     const uint32_t b = blockIdx.x * (kDecodeThreads / 32) + (threadIdx.x >> 5);
     if (b >= a.nblk) return;
@@ -163,7 +324,7 @@ lz4_decompress_kernel(DecodeArgs a)
         warp_copy(out, payload, csize, lane);
         r = (int32_t)csize;
     } else {
-        r = decode_block<kDict>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane);
+        r = decode_block<kDict>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane, s_bitmap[threadIdx.x >> 5]);
     }
     if (lane == 0) a.out_len[b] = r;
 }
