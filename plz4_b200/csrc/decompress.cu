@@ -173,15 +173,18 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                 const uint32_t dl = 3u + (tok >> 4) + ((tok & 15u) == 15u ? 1u : 0u);
                 dpack |= dl << (8 * i);
             }
-            // walk the chain: qb = byte offset inside the window
+            // walk the chain through shared memory (one byte load per sequence): qb = byte offset inside the window
+            bitmap[lane] = dpack;
+            __syncwarp();
+            const uint8_t* dl8 = reinterpret_cast<const uint8_t*>(bitmap);
             uint32_t qb = a0 & 3u;
             uint32_t myq = 0;
             while (nseq < 32 && qb <= 128u - 20u) {
                 if (lane == nseq) myq = qb;
-                const uint32_t dl = (__shfl_sync(FULL_MASK, dpack, qb >> 2) >> ((qb & 3u) * 8u)) & 0xFFu;
-                qb += dl;
+                qb += dl8[qb];
                 nseq++;
             }
+            __syncwarp();
             // each lane decodes its own header from the window
             auto wbyte = [&](uint32_t bo) -> uint32_t {        // byte at window offset bo (< 128)
                 return (__shfl_sync(FULL_MASK, w, bo >> 2) >> ((bo & 3u) * 8u)) & 0xFFu;
@@ -256,8 +259,9 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                     uint32_t val = 0;
                     if (live && !fwd) {
                         const int s = out0 + sr;
-                        const uint8_t* from = is_lit ? src + kp + d : ((kDict && s < 0) ? dict + dsz + s : dst + s);
-                        val = *from;
+                        if (is_lit) val = src[kp + d];
+                        else if (kDict && s < 0) val = dict[dsz + s];
+                        else val = dst[s];
                     }
                     if (__any_sync(FULL_MASK, fwd)) {
                         // forward values along in-chunk chains: root = the lane whose loaded value this byte finally equals
