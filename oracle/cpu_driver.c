@@ -116,3 +116,59 @@ DRV_API int drv_decompress_blocks(void* decompress_safe, void* xxh32, const uint
     j.bsz = bsz; j.checksum = checksum; j.dst = dst; j.out_len = out_len;
     return run(&j, nthreads);
 }
+
+/* ------------------------------------------------------------------ dictionary path (BASELINE configs[3])
+ * plz4.CompressBlock(src, WithBlockDictionary(d)) per payload, amortised form: the dictionary context is built
+ * once (clz4.NewDictCtx, clz4.go:101-120) and every worker keeps one LZ4_stream_t, doing exactly
+ * StreamIndieCtx.Compress (clz4.go:160-179): resetStream_fast + attach_dictionary + compress_fast_continue. */
+typedef void (*lz4_reset_fast_fn)(void* strm);
+typedef void (*lz4_attach_fn)(void* strm, const void* dict_strm);
+typedef int (*lz4_continue_fn)(void* strm, const char* src, char* dst, int n, int cap, int accel);
+
+typedef struct {
+    lz4_reset_fast_fn reset; lz4_attach_fn attach; lz4_continue_fn cont;
+    const void* dict_strm;
+    const uint8_t* src; const uint64_t* off; uint32_t msg, nmsg, slot;
+    uint8_t* dst; uint32_t* out_len;
+    atomic_uint next;
+} djob_t;
+
+static void* dworker(void* arg)
+{
+    djob_t* j = (djob_t*)arg;
+    /* LZ4_stream_t is 16416 bytes (lz4.h:719-727) */
+    static __thread long long strm[(16416 + 7) / 8];
+    memset(strm, 0, sizeof strm);
+    for (;;) {
+        uint32_t b = atomic_fetch_add(&j->next, 64);
+        if (b >= j->nmsg) break;
+        uint32_t e = b + 64 < j->nmsg ? b + 64 : j->nmsg;
+        for (; b < e; b++) {
+            j->reset(strm);
+            j->attach(strm, j->dict_strm);
+            j->out_len[b] = (uint32_t)j->cont(strm, (const char*)j->src + j->off[b], (char*)j->dst + (uint64_t)b * j->slot,
+                                             (int)j->msg, (int)j->slot, 1);
+        }
+    }
+    return NULL;
+}
+
+DRV_API int drv_compress_dict_msgs(void* reset_fast, void* attach, void* cont, const void* dict_strm,
+                                   const uint8_t* src, const uint64_t* off, uint32_t msg_len, uint32_t nmsg,
+                                   uint8_t* dst, uint32_t slot, uint32_t* out_len, int nthreads)
+{
+    djob_t j;
+    pthread_t th[256];
+    int i;
+    memset(&j, 0, sizeof j);
+    j.reset = (lz4_reset_fast_fn)reset_fast; j.attach = (lz4_attach_fn)attach; j.cont = (lz4_continue_fn)cont;
+    j.dict_strm = dict_strm; j.src = src; j.off = off; j.msg = msg_len; j.nmsg = nmsg; j.dst = dst; j.slot = slot;
+    j.out_len = out_len;
+    atomic_init(&j.next, 0);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    for (i = 1; i < nthreads; i++) pthread_create(&th[i], NULL, dworker, &j);
+    dworker(&j);
+    for (i = 1; i < nthreads; i++) pthread_join(th[i], NULL);
+    return 0;
+}

@@ -409,9 +409,9 @@ static cudaError_t set_smem_attr()
 
 int compress_hash_bits(uint32_t dst_cap)
 {
-    // blocks above 64 KiB come in small numbers (64 per 256 MiB at 4 MiB): occupancy is not the limit there,
+    // blocks above 1 MiB come in small numbers (64 per 256 MiB at 4 MiB): occupancy is not the limit there,
     // so they get liblz4's 8192-entry table back
-    return (dst_cap > 65536u + 65536u / 255u + 16u) ? 13 : g_hash_bits;
+    return (dst_cap > (1u << 20) + (1u << 20) / 255u + 16u) ? 13 : g_hash_bits;
 }
 
 cudaError_t configure_compress()

@@ -46,6 +46,7 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess)
 constexpr int kMaxLanes = 8;
 int kLanes = 4;                                  // lanes in use                   (PLZ4CU_LANES)
 uint32_t kChunkBlocks = 2048;                    // blocks per chunk we aim for    (PLZ4CU_CHUNK_BLOCKS)
+const uint64_t kChunkMinBytes = 64ull << 20;     // ... but small payloads are gathered up to this many bytes
 const uint64_t kChunkBytes = 512ull << 20;       // upper bound on a chunk's input span
 
 void read_tuning_env()
@@ -373,7 +374,7 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         Chunk c{b, b, src_off[b], src_off[b] + src_len[b]};
         while (c.b1 < nblk) {
             uint64_t lo = std::min(c.lo, src_off[c.b1]), hi = std::max(c.hi, src_off[c.b1] + src_len[c.b1]);
-            if (c.b1 > c.b0 && (hi - lo > kChunkBytes || c.b1 - c.b0 >= kChunkBlocks)) break;
+            if (c.b1 > c.b0 && (hi - lo > kChunkBytes || (c.b1 - c.b0 >= kChunkBlocks && c.hi - c.lo >= kChunkMinBytes))) break;
             c.lo = lo; c.hi = hi; c.b1++;
         }
         chunks.push_back(c);
@@ -479,7 +480,8 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
     };
 
     std::vector<Chunk> chunks;
-    const uint32_t max_blk_per_chunk = (uint32_t)std::min<uint64_t>(kChunkBlocks, std::max<uint64_t>(1, kChunkBytes / std::max<uint32_t>(dst_cap, 1)));
+    const uint32_t max_blk_per_chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(kChunkBlocks, kChunkMinBytes / std::max<uint32_t>(dst_cap, 1)),
+                                                                    std::max<uint64_t>(1, kChunkBytes / std::max<uint32_t>(dst_cap, 1)));
     for (uint32_t b = 0; b < nblk;) {
         uint64_t lo, hi;
         if (int r = rec_extent(b, &lo, &hi)) return r;

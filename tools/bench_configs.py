@@ -1,0 +1,118 @@
+#!/usr/bin/env python3
+"""Secondary measurements: the BASELINE.json configs that are NOT the headline bench line, scaled to
+minutes, GPU engine next to the reference's liblz4 on all host cores.  Prints one JSON object.
+These are reported context (profiles/r01_configs.json), not bench.py lines."""
+import ctypes as C, io, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import plz4_b200 as P
+from plz4_b200 import _lib
+from plz4_b200._lib import check
+from oracle import oracle as O
+from tests.datagen import make
+
+L = _lib.lib(); P.init(0)
+ref, port = O.Ref(), O.Port()
+drv = C.CDLL(os.path.join(os.path.dirname(O.__file__), "cpu_driver.so"))
+ncpu = os.cpu_count()
+vp = lambda a: C.c_void_p(a.ctypes.data)
+fn = lambda f: C.cast(f, C.c_void_p)
+res = {"host_cores": ncpu}
+
+def logtext(n, seed=0x504C5A34):
+    a = np.empty(n, dtype=np.uint8); L.plz4cu_gen_logtext_host(seed, 0, vp(a), n); return a
+
+def best(f, reps=3):
+    f(); t = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); f(); t.append(time.perf_counter() - t0)
+    return min(t)
+
+def cpu_blocks(data, bsz, checksum=1):
+    n = data.size; nblk = (n + bsz - 1) // bsz
+    recs = np.empty(nblk * (bsz + 8), dtype=np.uint8); rl = np.zeros(nblk, dtype=np.uint32)
+    out = np.empty(nblk * bsz, dtype=np.uint8); ol = np.zeros(nblk, dtype=np.uint32)
+    roff = np.arange(nblk, dtype=np.uint64) * (bsz + 8)
+    drv.drv_compress_blocks.argtypes = [C.c_void_p] * 3 + [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    drv.drv_decompress_blocks.argtypes = [C.c_void_p] * 5 + [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    tc = best(lambda: drv.drv_compress_blocks(fn(ref.lib.LZ4_compress_fast), fn(port.lib.orc_xxh32), vp(data), n, bsz, checksum, vp(recs), vp(rl), ncpu))
+    td = best(lambda: drv.drv_decompress_blocks(fn(ref.lib.LZ4_decompress_safe), fn(port.lib.orc_xxh32), vp(recs), vp(roff), vp(rl), nblk, bsz, checksum, vp(out), vp(ol), ncpu))
+    return n / tc / 1e9, n / td / 1e9, int(rl.sum()) / n
+
+# ---- configs[0]: 256 MiB log text, 4 MiB blocks, block + content checksums, host-resident streams
+data = logtext(256 << 20)
+raw = data.tobytes()
+def wr():
+    dst = io.BytesIO(); w = P.NewWriter(dst, block_size_idx=7, block_checksum=True, content_checksum=True, parallel=-1)
+    w.write(raw); w.close(); return dst.getvalue()
+frame = wr()
+def rd():
+    r = P.NewReader(io.BytesIO(frame), parallel=-1); out = io.BytesIO(); r.write_to(out); r.close(); return out.getvalue()
+assert rd() == raw
+tw, tr = best(lambda: wr(), 2), best(lambda: rd(), 2)
+cc, cd, cr = cpu_blocks(data, 4 << 20)
+res["config0_256MiB_4MiB_blocks_bx_cx_streams"] = {
+    "gpu_write_gbs": round(len(raw) / tw / 1e9, 2), "gpu_read_gbs": round(len(raw) / tr / 1e9, 2), "gpu_ratio": round(len(frame) / len(raw), 4),
+    "cpu_compress_gbs": round(cc, 2), "cpu_decompress_gbs": round(cd, 2), "cpu_ratio": round(cr, 4),
+    "note": "4 MiB blocks give 64 blocks = 64 warps: the GPU path is parallelism-starved here (DESIGN.md 6b)"}
+
+# ---- configs[2]: decode reference-produced frames (4 MiB blocks, bx) from random WithReadOffset starts
+from oracle import frame_oracle as F
+sub = raw[: 64 << 20]
+marks = []
+rframe = F.write_frame(sub, F.Opts(block_idx=7, block_checksum=True, content_checksum=False), port, progress=lambda s, d: marks.append((s, d)))
+rng = np.random.default_rng(3)
+picks = [marks[i] for i in rng.integers(0, len(marks) - 1, size=4)]
+def ra():
+    tot = 0
+    for s, d in picks:
+        r = P.NewReader(io.BytesIO(rframe), read_offset=d); tot += len(r.read_all()); r.close()
+    return tot
+tot = ra(); t3 = best(ra, 2)
+res["config2_random_access_reference_frames_4MiB"] = {"starts": len(picks), "decoded_bytes": tot, "gpu_gbs": round(tot / t3 / 1e9, 2)}
+
+# ---- configs[3]: 4 KiB payloads + 64 KiB dictionary, one batch call (device work + PCIe), vs liblz4 amortised dict ctx
+corpus = logtext(64 << 20, seed=13)
+nmsg = 1 << 18
+starts = rng.integers(65536, corpus.size - 4096, size=nmsg).astype(np.uint64)
+d = corpus[:65536].tobytes()
+gd = P.Dict(d)
+lens = np.full(nmsg, 4096, dtype=np.uint32)
+hsrc = torch.from_numpy(corpus).pin_memory()
+cap = P.compress_block_bound(4096)
+packed = torch.empty(nmsg * (cap + 8), dtype=torch.uint8).pin_memory(); poff = np.zeros(nmsg + 1, dtype=np.uint64)
+hp = lambda t: C.c_void_p(t.data_ptr())
+comp = lambda: check(L.plz4cu_compress_batch_host(hp(hsrc), vp(starts), vp(lens), nmsg, cap, 0, 1, gd.handle, hp(packed), packed.numel(), vp(poff)))
+t4c = best(comp)
+sizes = np.diff(poff).astype(np.uint32)
+out = torch.empty(nmsg * 4096, dtype=torch.uint8).pin_memory(); rs = np.zeros(nmsg, dtype=np.int32)
+dec = lambda: check(L.plz4cu_decompress_batch_host(hp(packed), int(poff[nmsg]), vp(poff), vp(sizes), nmsg, 4096, 0, 1, gd.handle, hp(out), 4096, vp(rs)))
+t4d = best(dec)
+assert (rs == 4096).all()
+rd_ = ref.dict_create(d)
+dst = np.empty(nmsg * cap, dtype=np.uint8); ol = np.zeros(nmsg, dtype=np.uint32)
+drv.drv_compress_dict_msgs.argtypes = [C.c_void_p] * 6 + [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+t4cpu = best(lambda: drv.drv_compress_dict_msgs(fn(ref.lib.LZ4_resetStream_fast), fn(ref.lib.LZ4_attach_dictionary), fn(ref.lib.LZ4_compress_fast_continue),
+                                                C.c_void_p(rd_._sp), vp(corpus), vp(starts), 4096, nmsg, vp(dst), cap, vp(ol), ncpu))
+res["config3_4KiB_payloads_64KiB_dict"] = {
+    "messages": nmsg, "gpu_compress_gbs": round(nmsg * 4096 / t4c / 1e9, 2), "gpu_compress_Mmsg_s": round(nmsg / t4c / 1e6, 2),
+    "gpu_decompress_gbs": round(nmsg * 4096 / t4d / 1e9, 2), "gpu_ratio": round(int(sizes.sum()) / (nmsg * 4096), 4),
+    "cpu_compress_gbs_amortised_dict_ctx": round(nmsg * 4096 / t4cpu / 1e9, 2), "cpu_ratio": round(int(ol.sum()) / (nmsg * 4096), 4),
+    "note": "host buffers, PCIe inside the timing; CPU figure keeps one dict ctx for all payloads (the reference rebuilds it per call)"}
+
+# ---- configs[4] in miniature: mixed-entropy stream, 256 KiB blocks, block + content checksum, NewWriter / NewReader
+seg = 1 << 20
+kinds = ["log", "log", "random", "zeros", "record1025", "log", "record1025", "log", "random", "log"]
+mixed = b"".join(make(kinds[i % 10], seg, seed=i) for i in range(256))
+def wr5():
+    dst = io.BytesIO(); w = P.NewWriter(dst, block_size_idx=5, block_checksum=True, content_checksum=True); w.write(mixed); w.close(); return dst.getvalue()
+f5 = wr5()
+def rd5():
+    r = P.NewReader(io.BytesIO(f5)); o = io.BytesIO(); r.write_to(o); r.close(); return o.getvalue()
+assert rd5() == mixed
+t5w, t5r = best(wr5, 2), best(rd5, 2)
+cc5, cd5, cr5 = cpu_blocks(np.frombuffer(mixed, dtype=np.uint8), 256 << 10)
+res["config4_mixed_256MiB_256KiB_blocks_bx_cx_streams"] = {
+    "gpu_write_gbs": round(len(mixed) / t5w / 1e9, 2), "gpu_read_gbs": round(len(mixed) / t5r / 1e9, 2), "gpu_ratio": round(len(f5) / len(mixed), 4),
+    "cpu_compress_gbs": round(cc5, 2), "cpu_decompress_gbs": round(cd5, 2), "cpu_ratio": round(cr5, 4)}
+print(json.dumps(res, indent=1))
