@@ -132,10 +132,14 @@ __device__ __noinline__ int decode_one(const uint8_t* __restrict__ src, int n, u
 
 // ---------------------------------------------------------------- batched decode
 
-template <bool kDict>
+// kRing: the last 64 KiB of output are mirrored in a shared-memory ring and match sources are read from there.
+// Used when a launch has too few blocks to hide global-memory latency with other warps (large block sizes):
+// the per-chunk round trip drops from an L2/HBM access to a shared-memory access.
+template <bool kDict, bool kRing>
 __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src, int n,
                                                 uint8_t* dst, int cap,
-                                                const uint8_t* __restrict__ dict, int dsz, int lane, uint32_t* bitmap)
+                                                const uint8_t* __restrict__ dict, int dsz, int lane, uint32_t* bitmap,
+                                                uint8_t* ring)
 {
     constexpr int kBatchBytes = 1024;               // output bytes one batch may span (32 bitmap words)
     if (cap == 0) return (n == 1 && src[0] == 0) ? 0 : -1;
@@ -261,7 +265,7 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                         const int s = out0 + sr;
                         if (is_lit) val = src[kp + d];
                         else if (kDict && s < 0) val = dict[dsz + s];
-                        else val = dst[s];
+                        else val = kRing ? ring[s & 0xFFFF] : dst[s];
                     }
                     if (__any_sync(FULL_MASK, fwd)) {
                         // forward values along in-chunk chains: root = the lane whose loaded value this byte finally equals
@@ -270,7 +274,10 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                         for (int it = 0; it < 5; it++) root = __shfl_sync(FULL_MASK, root, root);
                         val = __shfl_sync(FULL_MASK, val, root);
                     }
-                    if (live) *dx = (uint8_t)val;
+                    if (live) {
+                        *dx = (uint8_t)val;
+                        if (kRing) ring[(out0 + xr) & 0xFFFF] = (uint8_t)val;
+                    }
                     __syncwarp();
                 }
                 ip = __shfl_sync(FULL_MASK, my_ipn, nseq - 1);
@@ -281,18 +288,28 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
 
         // ---- anything that is not a shortcut sequence: one sequence through the literal state machine
         int32_t ret = 0;
+        const int op_before = op;
         if (decode_one<kDict>(src, n, dst, cap, dict, dsz, lane, ip, op, ret) == kStepDone) return ret;
         __syncwarp();                                   // its stores may be the next batch's match sources
+        if (kRing) {
+            // decode_one works on global memory: mirror what it produced into the ring
+            for (int k = max(op_before, op - 65536) + lane; k < op; k += 32) ring[k & 0xFFFF] = dst[k];
+            __syncwarp();
+        }
     }
 }
 
-template <bool kDict>
+template <bool kDict, bool kRing>
 __global__ void __launch_bounds__(kDecodeThreads)
 lz4_decompress_kernel(DecodeArgs a)
 {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];              // kRing: 64 KiB per warp
     __shared__ uint32_t s_bitmap[kDecodeThreads / 32][32];
     const int lane = lane_id();
-    const uint32_t b = blockIdx.x * (kDecodeThreads / 32) + (threadIdx.x >> 5);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t wpb = kRing ? 1u : (uint32_t)(kDecodeThreads / 32);
+    if (kRing && warp != 0) return;
+    const uint32_t b = blockIdx.x * wpb + warp;
     if (b >= a.nblk) return;
 
     const uint8_t* rec = a.rec_base + a.rec_off[b];
@@ -328,18 +345,36 @@ lz4_decompress_kernel(DecodeArgs a)
         warp_copy(out, payload, csize, lane);
         r = (int32_t)csize;
     } else {
-        r = decode_block<kDict>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane, s_bitmap[threadIdx.x >> 5]);
+        r = decode_block<kDict, kRing>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane,
+                                       s_bitmap[warp], dyn_smem);
     }
     if (lane == 0) a.out_len[b] = r;
+}
+
+constexpr uint32_t kRingBlocks = 1024;          // launches with fewer blocks than this use the ring kernel
+constexpr int kRingBytes = 65536;
+
+cudaError_t configure_decompress()
+{
+    cudaError_t e = cudaFuncSetAttribute(lz4_decompress_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lz4_decompress_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
 }
 
 cudaError_t launch_decompress(const DecodeArgs& a, cudaStream_t stream)
 {
     if (a.nblk == 0) return cudaSuccess;
+    if (a.nblk < kRingBlocks && a.dst_cap > 65536u) {
+        // few, large blocks: one warp per CTA with a shared-memory window (up to 3 CTAs per SM)
+        dim3 grid(a.nblk), block(32);
+        if (a.dict_size > 0) lz4_decompress_kernel<true, true><<<grid, block, kRingBytes, stream>>>(a);
+        else lz4_decompress_kernel<false, true><<<grid, block, kRingBytes, stream>>>(a);
+        return cudaGetLastError();
+    }
     const uint32_t wpb = kDecodeThreads / 32;
     dim3 grid((a.nblk + wpb - 1) / wpb), block(kDecodeThreads);
-    if (a.dict_size > 0) lz4_decompress_kernel<true><<<grid, block, 0, stream>>>(a);
-    else lz4_decompress_kernel<false><<<grid, block, 0, stream>>>(a);
+    if (a.dict_size > 0) lz4_decompress_kernel<true, false><<<grid, block, 0, stream>>>(a);
+    else lz4_decompress_kernel<false, false><<<grid, block, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

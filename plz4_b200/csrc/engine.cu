@@ -71,6 +71,8 @@ int ensure_configured()
     if (std::find(done.begin(), done.end(), dev) != done.end()) return 0;
     e = configure_compress();
     if (e != cudaSuccess) return fail(PLZ4CU_ERR_CUDA, "configure_compress", e);
+    e = configure_decompress();
+    if (e != cudaSuccess) return fail(PLZ4CU_ERR_CUDA, "configure_decompress", e);
     done.push_back(dev);
     return 0;
 }

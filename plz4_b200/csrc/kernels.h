@@ -25,6 +25,7 @@ struct DecodeArgs {
     int32_t* out_len;
 };
 cudaError_t launch_decompress(const DecodeArgs& a, cudaStream_t stream);
+cudaError_t configure_decompress();   // one-time function attributes (opt-in shared memory)
 
 struct EncodeArgs {
     const uint8_t* src_base;
