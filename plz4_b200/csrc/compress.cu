@@ -74,10 +74,16 @@ __device__ __noinline__ int emit_long(uint8_t* o, const uint8_t* __restrict__ li
 // kDict: the block may reference a read-only dictionary (a4: compress/indie.go:14-35, clz4.go:160-179).
 // Positions then live in a virtual space where the dictionary ends at 65536 and the block starts there;
 // the table starts as a copy of the dictionary's table instead of empty.
-template <int kHashBits, bool kDict>
+//
+// kFrag: the input is one 64 KiB fragment of a larger block (see lz4_compress_frag_kernel).  `prefix` bytes of the
+// same block precede src[0] in memory and may be matched (the table is pre-warmed with the last kPrewarm of
+// them); the final literal run is NOT emitted — its length goes to *tail_out and the stitcher merges it into the
+// next fragment's first sequence.
+template <int kHashBits, bool kDict, bool kFrag>
 __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int n, uint8_t* dst,
                                             int cap, uint16_t* table, int lane,
-                                            const uint8_t* __restrict__ dict, int dsz, const uint16_t* __restrict__ dict_table)
+                                            const uint8_t* __restrict__ dict, int dsz, const uint16_t* __restrict__ dict_table,
+                                            int prefix, uint32_t* tail_out)
 {
     constexpr uint32_t kEmpty = 0xFFFFu;
     constexpr int kProbe = 15;                       // bytes of every candidate examined in parallel
@@ -107,11 +113,23 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
         const uint32_t d16 = (uint32_t)sa & 15u;
         const uint32_t end16 = (d16 + (uint32_t)n + 15u) >> 4;       // 16-byte chunks holding valid bytes
         const uint32_t last4 = (d16 + (uint32_t)n - 1u) >> 2;        // last word holding a valid byte
-        auto own4 = [&](int q) -> uint32_t {                          // 4 bytes at position q (q < ld_end)
-            const uint32_t a = d16 + (uint32_t)q;
-            const uint32_t lo = src4[a >> 2], hi = src4[min((a >> 2) + 1u, last4)];
-            return __funnelshift_r(lo, hi, (a & 3u) * 8u);
+        auto own4 = [&](int q) -> uint32_t {                          // 4 bytes at position q (-prefix <= q < ld_end)
+            const int a = (int)d16 + q;
+            const uint32_t lo = src4[a >> 2], hi = src4[min((a >> 2) + 1, (int)last4)];
+            return __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8u);
         };
+        if (kFrag && prefix > 0) {
+            // pre-warm: the last kPrewarm bytes of the previous fragment enter the table (no candidates wanted yet)
+            constexpr int kPrewarm = 16384;
+            for (int q0 = -min(prefix, kPrewarm); q0 < 0; q0 += 32) {
+                const int q = q0 + lane;
+                const uint32_t hv = (own4(q) * 2654435761u) >> (32 - kHashBits);
+                const uint32_t same = __match_any_sync(FULL_MASK, hv);
+                if ((same >> lane) == 1u) table[hv] = (uint16_t)q;
+            }
+            __syncwarp();
+        }
+        const int lo_cand = kFrag ? 1 - min(prefix, 65535) : 1;      // lowest usable candidate position
         const uintptr_t da = reinterpret_cast<uintptr_t>(dict);
         const uint4* __restrict__ dict16 = reinterpret_cast<const uint4*>(da & ~uintptr_t(15));
         const uint32_t dd16 = (uint32_t)da & 15u;
@@ -128,7 +146,7 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
 
             // ---- (a1) hash, table lookup, same-group duplicates, table update
             uint32_t h = 0x80000000u | (uint32_t)lane;
-            int cand = -1;
+            int cand = -0x40000000;                               // "none": fails the distance test below
             if (valid) {
                 h = (v * 2654435761u) >> (32 - kHashBits);
                 const uint32_t c = table[h];
@@ -150,17 +168,17 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             const bool in_dict = kDict && cand < 0;
             const int didx = cand + dsz;                              // index inside the dictionary when in_dict
             const bool want = valid && p >= anchor && (uint32_t)(p - cand) <= MAX_DISTANCE &&
-                              (in_dict ? didx >= 1 : cand >= 1);
+                              (in_dict ? didx >= 1 : cand >= lo_cand);
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
             uint32_t t = 0;
             if (want) {
                 // fetch starts at the byte before the candidate
-                const uint32_t ca = in_dict ? (dd16 + (uint32_t)didx - 1u) : (d16 + (uint32_t)cand - 1u);
+                const int ca = in_dict ? ((int)dd16 + didx - 1) : ((int)d16 + cand - 1);   // may be negative in a fragment
                 const uint4* __restrict__ cb16 = in_dict ? dict16 : src16;
-                const uint32_t ci = ca >> 4;
-                t = ca & 15u;
+                const int ci = ca >> 4;
+                t = (uint32_t)(ca & 15);
                 r0 = cb16[ci];
-                if (in_dict || ci + 1 < end16) r1 = cb16[ci + 1];    // the dictionary buffer carries 32 B of zeroed slack
+                if (in_dict || ci + 1 < (int)end16) r1 = cb16[ci + 1];    // the dictionary buffer carries 32 B of zeroed slack
             }
             // own bytes p-1 .. p+14 as four words, from the neighbours' registers
             uint32_t o0, o1, o2, o3;
@@ -313,6 +331,10 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             }
         }
     }
+    if (kFrag) {
+        *tail_out = (uint32_t)(n - anchor);          // the stitcher owns the final literal run
+        return op;
+    }
     // last literals (lz4.c:1302-1329)
     {
         const int run = n - anchor;
@@ -328,28 +350,13 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
     return op;
 }
 
-template <int kHashBits, bool kDict>
-__global__ void __launch_bounds__(kEncodeWarps * 32, 6)
-lz4_compress_kernel(EncodeArgs a)
+// blk.CompressToBlk's framing around an encoded payload of c bytes (c == 0: it did not fit): stored fallback,
+// size word, xxh32 trailer, record length (blk/blk.go:78-106); raw block API: just the length (clz4.go:40-42).
+__device__ __forceinline__ void finish_record(const EncodeArgs& a, uint32_t b, const uint8_t* src, int n,
+                                              uint8_t* rec, uint8_t* payload, int c, int lane)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kTableBytes = 2 << kHashBits;      // u16[1 << bits]
-    const int lane = lane_id();
-    const int warp = threadIdx.x >> 5;
-    const uint32_t b = blockIdx.x * kEncodeWarps + warp;
-    if (b >= a.nblk) return;
-
-    const uint8_t* src = a.src_base + a.src_off[b];
-    const int n = (int)a.src_len[b];
-    uint8_t* rec = a.rec_base + (uint64_t)b * a.rec_stride;
-    uint8_t* payload = a.raw_blocks ? rec : rec + 4;
-    uint16_t* table = reinterpret_cast<uint16_t*>(smem + warp * kTableBytes);
-
-    int c = encode_block<kHashBits, kDict>(src, n, payload, (int)a.dst_cap, table, lane, a.dict, (int)a.dict_size,
-                                           a.dict_table);
-
     if (a.raw_blocks) {
-        if (lane == 0) a.rec_len[b] = (uint32_t)c;      // 0 = does not fit (clz4.go:40-42)
+        if (lane == 0) a.rec_len[b] = (uint32_t)c;      // 0 = does not fit
         return;
     }
     uint32_t word;
@@ -369,6 +376,160 @@ lz4_compress_kernel(EncodeArgs a)
         total += 4;
     }
     if (lane == 0) a.rec_len[b] = total;
+}
+
+template <int kHashBits, bool kDict>
+__global__ void __launch_bounds__(kEncodeWarps * 32, 6)
+lz4_compress_kernel(EncodeArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int kTableBytes = 2 << kHashBits;      // u16[1 << bits]
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x * kEncodeWarps + warp;
+    if (b >= a.nblk) return;
+
+    const uint8_t* src = a.src_base + a.src_off[b];
+    const int n = (int)a.src_len[b];
+    uint8_t* rec = a.rec_base + (uint64_t)b * a.rec_stride;
+    uint8_t* payload = a.raw_blocks ? rec : rec + 4;
+    uint16_t* table = reinterpret_cast<uint16_t*>(smem + warp * kTableBytes);
+
+    int c = encode_block<kHashBits, kDict, false>(src, n, payload, (int)a.dst_cap, table, lane, a.dict, (int)a.dict_size,
+                                                  a.dict_table, 0, nullptr);
+    finish_record(a, b, src, n, rec, payload, c, lane);
+}
+
+// ---------------------------------------------------------------- blocks larger than 64 KiB
+//
+// One warp per block would leave a 4 MiB-block frame (plz4's default) with 64 blocks of parallelism per 256 MiB.
+// The encoder is free to choose its parse, so a large block is cut into 64 KiB FRAGMENTS, each encoded by its own
+// warp (matches may reach back into the previous fragment: same block, same window rules), and a stitch pass joins
+// the fragment streams into one LZ4 block: the literals left over at the end of fragment k become part of the first
+// sequence of fragment k+1, so only that sequence's token / length bytes are rewritten; everything else is copied.
+constexpr int kFragBytes = 65536;
+
+struct FragArgs {
+    EncodeArgs e;
+    uint8_t* tmp;              // [nblk * frags_per_block] slots of frag_stride bytes
+    uint32_t frag_stride;
+    uint32_t frags_per_block;
+    int32_t* frag_len;         // encoded bytes before the final literal run; -2 = fragment does not exist
+    uint32_t* frag_tail;       // literal bytes left over at the fragment's end
+};
+
+template <int kHashBits>
+__global__ void __launch_bounds__(kEncodeWarps * 32, 6)
+lz4_compress_frag_kernel(FragArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int kTableBytes = 2 << kHashBits;
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * kEncodeWarps + warp;
+    const uint32_t b = w / a.frags_per_block, f = w % a.frags_per_block;
+    if (b >= a.e.nblk) return;
+    const int n_blk = (int)a.e.src_len[b];
+    const int start = (int)f * kFragBytes;
+    if (start >= n_blk && f != 0) {
+        if (lane == 0) a.frag_len[w] = -2;
+        return;
+    }
+    const int n = min(kFragBytes, n_blk - start);
+    const uint8_t* src = a.e.src_base + a.e.src_off[b] + start;
+    uint16_t* table = reinterpret_cast<uint16_t*>(smem + warp * kTableBytes);
+    uint32_t tail = 0;
+    int c = encode_block<kHashBits, false, true>(src, n, a.tmp + (uint64_t)w * a.frag_stride, (int)a.frag_stride, table, lane,
+                                                 nullptr, 0, nullptr, start, &tail);
+    if (lane == 0) { a.frag_len[w] = c; a.frag_tail[w] = tail; }
+}
+
+constexpr int kStitchWarps = 8;
+constexpr int kMaxFrags = 66;                     // 4 MiB / 64 KiB (+ CompressBound slack on the raw block path)
+
+// One CTA per block.  Warp 0 plans (a short serial walk over <= 64 fragments: new first-token header and output
+// offset of each), all warps copy fragments in parallel, warp 0 writes the last literals and frames the record.
+__global__ void __launch_bounds__(kStitchWarps * 32)
+lz4_stitch_kernel(FragArgs a)
+{
+    __shared__ int s_out[kMaxFrags];              // output offset of the fragment's (rewritten) first token; -1 = skip
+    __shared__ int s_carry[kMaxFrags];            // literals carried into the fragment
+    __shared__ int s_pos[kMaxFrags];              // source position of the fragment
+    __shared__ int s_end, s_tail, s_ok;
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x;
+    const uint8_t* src = a.e.src_base + a.e.src_off[b];
+    const int n_blk = (int)a.e.src_len[b];
+    uint8_t* rec = a.e.rec_base + (uint64_t)b * a.e.rec_stride;
+    uint8_t* out = a.e.raw_blocks ? rec : rec + 4;
+    const int cap = (int)a.e.dst_cap;
+    const int F = (int)a.frags_per_block;
+
+    if (warp == 0) {
+        int op = 0, carry = 0, pos = 0;
+        bool ok = true;
+        for (int f = 0; f < F; f++) {
+            const uint32_t w = b * a.frags_per_block + (uint32_t)f;
+            const int flen = a.frag_len[w];
+            if (flen == -2) { for (int g = f + lane; g < F; g += 32) s_out[g] = -1; break; }
+            const int nf = min(kFragBytes, n_blk - pos);
+            if (flen <= 0) {                                            // no sequence in this fragment: all literals
+                if (lane == 0) s_out[f] = -1;
+                carry += nf; pos += nf;
+                continue;
+            }
+            const uint8_t* frag = a.tmp + (uint64_t)w * a.frag_stride;
+            const uint32_t tok = frag[0];
+            int l0 = (int)(tok >> 4), hdr0 = 1;
+            if (l0 == 15) { uint32_t s; do { s = frag[hdr0++]; l0 += (int)s; } while (s == 255); }
+            const int L = carry + l0;
+            const int need = 1 + (L >= 15 ? ext_bytes(L - 15) : 0) + carry + (flen - hdr0);
+            if (op + need > cap) { ok = false; break; }
+            if (lane == 0) { s_out[f] = op; s_carry[f] = carry; s_pos[f] = pos; }
+            op += need;
+            carry = (int)a.frag_tail[w];
+            pos += nf;
+        }
+        if (ok && op + 1 + (carry >= 15 ? ext_bytes(carry - 15) : 0) + carry > cap) ok = false;
+        if (lane == 0) { s_end = op; s_tail = carry; s_ok = ok ? 1 : 0; }
+    }
+    __syncthreads();
+    if (s_ok) {
+        for (int f = warp; f < F; f += kStitchWarps) {
+            int op = s_out[f];
+            if (op < 0) continue;
+            const uint32_t w = b * a.frags_per_block + (uint32_t)f;
+            const uint8_t* frag = a.tmp + (uint64_t)w * a.frag_stride;
+            const int flen = a.frag_len[w], carry = s_carry[f];
+            const uint32_t tok = frag[0];
+            int l0 = (int)(tok >> 4), hdr0 = 1;
+            if (l0 == 15) { uint32_t s; do { s = frag[hdr0++]; l0 += (int)s; } while (s == 255); }
+            const int L = carry + l0;
+            // the fragment's first sequence: its literal run grows by the literals carried over
+            if (lane == 0) out[op] = (uint8_t)(((L < 15 ? L : 15) << 4) | (tok & 15u));
+            op += 1;
+            if (L >= 15) { put_ext(out + op, L - 15, lane); op += ext_bytes(L - 15); }
+            warp_copy(out + op, src + s_pos[f] - carry, (uint32_t)carry, lane);
+            op += carry;
+            warp_copy(out + op, frag + hdr0, (uint32_t)(flen - hdr0), lane);   // own literals, offset, length bytes, later sequences
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    int c = 0;
+    if (s_ok) {
+        // last literals of the block (lz4.c:1302-1329)
+        int op = s_end;
+        const int carry = s_tail;
+        if (lane == 0) out[op] = (uint8_t)((carry < 15 ? carry : 15) << 4);
+        op += 1;
+        if (carry >= 15) { put_ext(out + op, carry - 15, lane); op += ext_bytes(carry - 15); }
+        warp_copy(out + op, src + n_blk - carry, (uint32_t)carry, lane);
+        c = op + carry;
+    }
+    __threadfence_block();
+    finish_record(a.e, b, src, n_blk, rec, out, c, lane);
 }
 
 // Dictionary table: for every hash the LAST dictionary position holding it (what a block would have seen
@@ -403,7 +564,10 @@ static cudaError_t set_smem_attr()
     cudaError_t e = cudaFuncSetAttribute(lz4_compress_kernel<kBits, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kEncodeWarps * (2 << kBits));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lz4_compress_kernel<kBits, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(lz4_compress_kernel<kBits, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kEncodeWarps * (2 << kBits));
+    if (e != cudaSuccess || kBits == 13) return e;
+    return cudaFuncSetAttribute(lz4_compress_frag_kernel<(kBits == 13 ? 12 : kBits)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kEncodeWarps * (2 << kBits));
 }
 
@@ -436,15 +600,56 @@ cudaError_t configure_compress()
         cudaError_t err = cudaMemcpyToSymbol(g_lazy_dev, &v, sizeof v);
         if (err != cudaSuccess) return err;
     }
+    {
+        // fragment scratch comes from the stream-ordered allocator: keep freed memory cached in the pool instead
+        // of handing it back to the driver at every synchronisation
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cudaError_t err = set_smem_attr<11>();
     if (err == cudaSuccess) err = set_smem_attr<12>();
     if (err == cudaSuccess) err = set_smem_attr<13>();
     return err;
 }
 
+template <int kBits>
+static cudaError_t launch_frag(const FragArgs& fa, uint32_t nwarps, cudaStream_t stream)
+{
+    lz4_compress_frag_kernel<kBits><<<(nwarps + kEncodeWarps - 1) / kEncodeWarps, kEncodeWarps * 32, kEncodeWarps * (2 << kBits), stream>>>(fa);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
 {
     if (a.nblk == 0) return cudaSuccess;
+    if (a.dst_cap > (uint32_t)kFragBytes + kFragBytes / 255u + 16u && a.dict_size == 0 &&
+        (a.dst_cap + kFragBytes - 1) / kFragBytes <= (uint32_t)kMaxFrags + 1) {
+        // large blocks: fragment-parallel encode + stitch; scratch comes from the stream-ordered allocator
+        FragArgs fa{};
+        fa.e = a;
+        fa.frags_per_block = (a.dst_cap + kFragBytes - 1) / kFragBytes;
+        fa.frag_stride = (uint32_t)((kFragBytes + kFragBytes / 255 + 16 + 15) & ~15);
+        const uint64_t nfrag = (uint64_t)a.nblk * fa.frags_per_block;
+        void* scratch = nullptr;
+        const uint64_t bytes = nfrag * fa.frag_stride + nfrag * 8;
+        cudaError_t e = cudaMallocAsync(&scratch, bytes, stream);
+        if (e != cudaSuccess) return e;
+        fa.tmp = static_cast<uint8_t*>(scratch);
+        fa.frag_len = reinterpret_cast<int32_t*>(fa.tmp + nfrag * fa.frag_stride);
+        fa.frag_tail = reinterpret_cast<uint32_t*>(fa.frag_len + nfrag);
+        const int bits = g_hash_bits == 11 ? 11 : 12;
+        e = (bits == 11) ? launch_frag<11>(fa, (uint32_t)nfrag, stream) : launch_frag<12>(fa, (uint32_t)nfrag, stream);
+        if (e == cudaSuccess) {
+            lz4_stitch_kernel<<<a.nblk, kStitchWarps * 32, 0, stream>>>(fa);
+            e = cudaGetLastError();
+        }
+        cudaError_t e2 = cudaFreeAsync(scratch, stream);
+        return e != cudaSuccess ? e : e2;
+    }
     dim3 grid((a.nblk + kEncodeWarps - 1) / kEncodeWarps), block(kEncodeWarps * 32);
     const int bits = compress_hash_bits(a.dst_cap);
     const size_t sm = (size_t)kEncodeWarps * (2u << bits);
