@@ -79,6 +79,8 @@ PLZ4CU_API size_t plz4cu_compress_bound(size_t n);
 /* Pinned host slabs: what blk.BorrowBlk/ReturnBlk (blk/pool.go:35-69) hand out in the GPU build. */
 PLZ4CU_API void* plz4cu_host_alloc(size_t n);
 PLZ4CU_API void plz4cu_host_free(void* p);
+/* Release the slabs the pool keeps cached for reuse (freed slabs are otherwise kept pinned, like a sync.Pool). */
+PLZ4CU_API void plz4cu_host_trim(void);
 /* Outstanding pinned slabs — the blk.CntBorrowed() leak gauge (blk/pool.go:29-33). */
 PLZ4CU_API int64_t plz4cu_host_outstanding(void);
 PLZ4CU_API void* plz4cu_device_alloc(size_t n);
@@ -281,6 +283,17 @@ PLZ4CU_API void plz4cu_reader_free(plz4cu_reader_t* r);
 
 /* plz4.WriteSkipFrameHeader (plz4_writer.go:56-62, header/skip.go:18-34): 8 bytes. */
 PLZ4CU_API int plz4cu_write_skip_frame_header(plz4cu_write_fn wr, void* wr_ctx, uint8_t nibble, uint32_t sz);
+
+/* In-memory endpoints for the stream callbacks (what bytes.Reader / bytes.Buffer are to the Go tests): a membuf
+ * wraps caller memory, never copies or frees it.  Reading consumes [pos, len); writing appends at len up to cap.
+ * Pass the membuf as the callback context together with plz4cu_membuf_read / _write / _seek. */
+typedef struct plz4cu_membuf plz4cu_membuf_t;
+PLZ4CU_API plz4cu_membuf_t* plz4cu_membuf_new(void* data, size_t len, size_t cap);
+PLZ4CU_API void plz4cu_membuf_free(plz4cu_membuf_t* m);
+PLZ4CU_API size_t plz4cu_membuf_len(const plz4cu_membuf_t* m);
+PLZ4CU_API int64_t plz4cu_membuf_read(void* ctx, void* buf, size_t n);
+PLZ4CU_API int64_t plz4cu_membuf_write(void* ctx, const void* data, size_t n);
+PLZ4CU_API int plz4cu_membuf_seek(void* ctx, int64_t delta);
 
 /* xxh32.ChecksumZero of a host buffer, computed on the host (header HC byte, content checksum). */
 PLZ4CU_API uint32_t plz4cu_xxh32_host(const void* p, size_t n);

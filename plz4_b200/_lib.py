@@ -33,6 +33,7 @@ SIGNATURES = {
     "plz4cu_compress_bound": (_sz, [_sz]),
     "plz4cu_host_alloc": (_vp, [_sz]),
     "plz4cu_host_free": (None, [_vp]),
+    "plz4cu_host_trim": (None, []),
     "plz4cu_host_outstanding": (C.c_int64, []),
     "plz4cu_device_alloc": (_vp, [_sz]),
     "plz4cu_device_free": (None, [_vp]),
@@ -67,6 +68,12 @@ SIGNATURES = {
     "plz4cu_reader_free": (None, [_vp]),
     "plz4cu_write_skip_frame_header": (_int, [_vp, _vp, C.c_uint8, _u32]),
     "plz4cu_xxh32_host": (_u32, [_vp, _sz]),
+    "plz4cu_membuf_new": (_vp, [_vp, _sz, _sz]),
+    "plz4cu_membuf_free": (None, [_vp]),
+    "plz4cu_membuf_len": (_sz, [_vp]),
+    "plz4cu_membuf_read": (C.c_int64, [_vp, _vp, _sz]),
+    "plz4cu_membuf_write": (C.c_int64, [_vp, _vp, _sz]),
+    "plz4cu_membuf_seek": (_int, [_vp, C.c_int64]),
 }
 
 WRITE_FN = C.CFUNCTYPE(C.c_int64, _vp, _vp, _sz)

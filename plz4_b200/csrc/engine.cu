@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <unordered_map>
 
 using namespace plz4;
 
@@ -23,6 +24,12 @@ static_assert(PLZ4CU_E_BLOCKHASH == PLZ4CU_E_BLOCKHASH_, "header/kernels mismatc
 static_assert(PLZ4CU_E_OVERFLOW == PLZ4CU_E_OVERFLOW_, "header/kernels mismatch");
 
 namespace {
+
+std::mutex g_slab_mu;
+std::unordered_map<void*, size_t> g_slab_size;                 // every live slab -> its size class
+std::unordered_map<size_t, std::vector<void*>> g_slab_free;    // cached, not borrowed
+size_t g_slab_cached = 0;
+const size_t kSlabCacheMax = 4ull << 30;
 
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
@@ -192,19 +199,61 @@ size_t plz4cu_compress_bound(size_t n)
     return n + n / 255 + 16;
 }
 
+// Pinned slabs are pooled by power-of-two size class: pinning is slow (~0.3 ms per MiB), and the reference hands its
+// blocks out of sync.Pools for the same reason (blk/pool.go:22-27).  Freed slabs stay cached for the next borrower.
 void* plz4cu_host_alloc(size_t n)
 {
+    size_t cls = 1u << 16;
+    while (cls < n) cls <<= 1;
+    {
+        std::lock_guard<std::mutex> lk(g_slab_mu);
+        auto it = g_slab_free.find(cls);
+        if (it != g_slab_free.end() && !it->second.empty()) {
+            void* p = it->second.back();
+            it->second.pop_back();
+            g_slab_cached -= cls;
+            g_host_outstanding++;
+            return p;
+        }
+    }
     void* p = nullptr;
-    cudaError_t e = cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&p, cls, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        plz4cu_host_trim();                      // give cached slabs back and retry once
+        e = cudaHostAlloc(&p, cls, cudaHostAllocDefault);
+    }
     if (e != cudaSuccess) { fail(PLZ4CU_ERR_NOMEM, "cudaHostAlloc", e); return nullptr; }
+    {
+        std::lock_guard<std::mutex> lk(g_slab_mu);
+        g_slab_size[p] = cls;
+    }
     g_host_outstanding++;
     return p;
 }
 void plz4cu_host_free(void* p)
 {
     if (!p) return;
-    cudaFreeHost(p);
     g_host_outstanding--;
+    std::lock_guard<std::mutex> lk(g_slab_mu);
+    auto it = g_slab_size.find(p);
+    if (it == g_slab_size.end()) { cudaFreeHost(p); return; }
+    const size_t cls = it->second;
+    if (g_slab_cached + cls > kSlabCacheMax) {
+        g_slab_size.erase(it);
+        cudaFreeHost(p);
+        return;
+    }
+    g_slab_free[cls].push_back(p);
+    g_slab_cached += cls;
+}
+void plz4cu_host_trim(void)
+{
+    std::lock_guard<std::mutex> lk(g_slab_mu);
+    for (auto& kv : g_slab_free) {
+        for (void* p : kv.second) { g_slab_size.erase(p); cudaFreeHost(p); }
+        kv.second.clear();
+    }
+    g_slab_cached = 0;
 }
 int64_t plz4cu_host_outstanding(void) { return g_host_outstanding.load(); }
 

@@ -91,6 +91,31 @@ int block_size_of(int idx)
 inline void put32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
 inline uint32_t get32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 
+// Grow-only pinned staging (blk.BorrowBlk's job in the GPU build): no zero-fill, DMA-able, counted by
+// plz4cu_host_outstanding() so the leak discipline of the reference's tests (wr_test.go:29-33) still has a gauge.
+struct PinnedBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    ~PinnedBuf() { release(); }
+    void release()
+    {
+        if (p) { if (pinned) plz4cu_host_free(p); else free(p); }
+        p = nullptr; cap = 0;
+    }
+    bool reserve(size_t n)
+    {
+        if (n <= cap) return true;
+        release();
+        // small streams are not worth pinning; large ones borrow a pooled pinned slab
+        pinned = n >= (4u << 20);
+        p = static_cast<uint8_t*>(pinned ? plz4cu_host_alloc(n) : malloc(std::max<size_t>(n, 64)));
+        if (!p) return false;
+        cap = n;
+        return true;
+    }
+};
+
 struct Opts {
     plz4cu_opts_t o;
     std::vector<uint8_t> dict;                        // owned copy (the caller's buffer need not outlive the call)
@@ -149,7 +174,7 @@ struct plz4cu_writer {
     std::vector<uint8_t> small;
     uint8_t* slab = nullptr;
     size_t fill = 0;
-    std::vector<uint8_t> packed;
+    PinnedBuf packed;
     std::vector<uint64_t> offs, poff;
     std::vector<uint32_t> lens;
 
@@ -211,23 +236,24 @@ struct plz4cu_writer {
         const uint32_t nblk = (uint32_t)((n + bsz - 1) / bsz);
         offs.resize(nblk); lens.resize(nblk); poff.resize(nblk + 1);
         for (uint32_t i = 0; i < nblk; i++) { offs[i] = (uint64_t)i * bsz; lens[i] = (uint32_t)std::min<size_t>(bsz, n - offs[i]); }
-        packed.resize((size_t)nblk * (bsz + 8));
+        const size_t packed_cap = (size_t)nblk * (bsz + 8);
+        if (!packed.reserve(packed_cap)) return PLZ4CU_Z_ENGINE;
         // the serial content checksum runs on a host core while the GPU works (async/hash.go)
         std::future<void> hf;
         if (opt.o.content_checksum) hf = std::async(std::launch::async, [&] { hasher.update(data, n); });
         int rc = plz4cu_compress_batch_host(data, offs.data(), lens.data(), nblk, (uint32_t)bsz, opt.o.block_checksum, 0, dict,
-                                            packed.data(), packed.size(), poff.data());
+                                            packed.p, packed_cap, poff.data());
         if (hf.valid()) hf.get();
         if (rc < 0) return PLZ4CU_Z_ENGINE;
         if (!opt.o.progress) {
             // nobody watches block boundaries: one write for the whole batch
-            if (int e = write_all(packed.data(), (size_t)poff[nblk], PLZ4CU_Z_WRITE)) return e;
+            if (int e = write_all(packed.p, (size_t)poff[nblk], PLZ4CU_Z_WRITE)) return e;
             src_mark += (int64_t)n; dst_mark += (int64_t)poff[nblk];
             return 0;
         }
         for (uint32_t i = 0; i < nblk; i++) {
             const size_t len = (size_t)(poff[i + 1] - poff[i]);
-            int e = write_all(packed.data() + poff[i], len, PLZ4CU_Z_WRITE);
+            int e = write_all(packed.p + poff[i], len, PLZ4CU_Z_WRITE);
             opt.o.progress(opt.o.progress_ctx, src_mark, dst_mark);        // async/writer.go:327-331
             src_mark += lens[i]; dst_mark += (int64_t)len;
             if (e) return e;
@@ -321,7 +347,8 @@ struct plz4cu_reader {
     XXH32 hasher;
 
     // current batch of decoded blocks
-    std::vector<uint8_t> recs, out;
+    PinnedBuf recs, out;
+    size_t recs_len = 0;
     std::vector<uint64_t> rec_off;
     std::vector<uint32_t> rec_read;                   // input bytes each block consumed (size word + body + hash)
     std::vector<int32_t> out_len;
@@ -453,8 +480,9 @@ struct plz4cu_reader {
     void fill_batch()
     {
         const size_t batch_blocks = std::max<size_t>(1, opt.batch_bytes(bsz) / (size_t)bsz);
-        recs.clear(); rec_off.clear(); rec_read.clear();
+        recs_len = 0; rec_off.clear(); rec_read.clear();
         nblk = 0; cur = 0; tail_event = 0; tail_read = 0;
+        if (!recs.reserve(batch_blocks * ((size_t)bsz + 8))) { tail_event = PLZ4CU_Z_ENGINE; return; }
         while (nblk < batch_blocks) {
             uint8_t w[4];
             size_t got = 0;
@@ -476,20 +504,20 @@ struct plz4cu_reader {
             uint32_t n = word & 0x7FFFFFFFu;
             if (n > (uint32_t)bsz) { tail_event = PLZ4CU_Z_BLOCK_SIZE_OVERFLOW; tail_read = 4; break; }
             const size_t body = (size_t)n + (blk_check ? 4 : 0);
-            const size_t at = recs.size();
-            recs.resize(at + 4 + body);
-            memcpy(recs.data() + at, w, 4);
-            r = read_full(recs.data() + at + 4, body, &got);
-            if (r != 0) { recs.resize(at); tail_event = PLZ4CU_Z_BLOCK_READ; tail_read = 4 + (uint32_t)got; break; }
+            const size_t at = recs_len;
+            memcpy(recs.p + at, w, 4);
+            r = read_full(recs.p + at + 4, body, &got);
+            if (r != 0) { tail_event = PLZ4CU_Z_BLOCK_READ; tail_read = 4 + (uint32_t)got; break; }
+            recs_len = at + 4 + body;
             rec_off.push_back(at);
             rec_read.push_back((uint32_t)(4 + body));
             nblk++;
         }
         if (nblk) {
-            out.resize((size_t)nblk * bsz);
             out_len.resize(nblk);
-            int rc = plz4cu_decompress_batch_host(recs.data(), recs.size(), rec_off.data(), nullptr, nblk, (uint32_t)bsz, blk_check, 0,
-                                                  dict, out.data(), (uint64_t)bsz, out_len.data());
+            int rc = out.reserve((size_t)nblk * bsz) ? 0 : -1;
+            if (rc == 0) rc = plz4cu_decompress_batch_host(recs.p, recs_len, rec_off.data(), nullptr, nblk, (uint32_t)bsz, blk_check, 0,
+                                                           dict, out.p, (uint64_t)bsz, out_len.data());
             if (rc < 0) { nblk = 0; tail_event = PLZ4CU_Z_ENGINE; }
         }
     }
@@ -511,7 +539,7 @@ struct plz4cu_reader {
             }
             cur_off = 0; cur_len = (size_t)r;
             dst_pos += r; content_acc += (uint64_t)r;
-            if (verify_content_hash) hasher.update(out.data() + (size_t)cur * bsz, (size_t)r);
+            if (verify_content_hash) hasher.update(out.p + (size_t)cur * bsz, (size_t)r);
             have_block = true;
             cur++;
             return 0;
@@ -526,7 +554,7 @@ struct plz4cu_reader {
         src_pos += tail_read;
         return ev;
     }
-    const uint8_t* block_ptr() const { return out.data() + (size_t)(cur - 1) * bsz; }
+    const uint8_t* block_ptr() const { return out.p + (size_t)(cur - 1) * bsz; }
 
     // rdr/rdr.go:91-101
     int handle_end_mark()
@@ -706,5 +734,38 @@ int plz4cu_write_skip_frame_header(plz4cu_write_fn wr, void* wr_ctx, uint8_t nib
 }
 
 uint32_t plz4cu_xxh32_host(const void* p, size_t n) { return xxh32_once(p, n); }
+
+// ---- in-memory endpoints (bytes.Reader / bytes.Buffer for C callers)
+struct plz4cu_membuf { uint8_t* data; size_t len, cap, pos; };
+plz4cu_membuf_t* plz4cu_membuf_new(void* data, size_t len, size_t cap)
+{
+    plz4cu_membuf* m = new plz4cu_membuf{static_cast<uint8_t*>(data), len, cap, 0};
+    return m;
+}
+void plz4cu_membuf_free(plz4cu_membuf_t* m) { delete m; }
+size_t plz4cu_membuf_len(const plz4cu_membuf_t* m) { return m->len; }
+int64_t plz4cu_membuf_read(void* ctx, void* buf, size_t n)
+{
+    plz4cu_membuf* m = static_cast<plz4cu_membuf*>(ctx);
+    size_t k = std::min(n, m->len - m->pos);
+    memcpy(buf, m->data + m->pos, k);
+    m->pos += k;
+    return (int64_t)k;
+}
+int64_t plz4cu_membuf_write(void* ctx, const void* data, size_t n)
+{
+    plz4cu_membuf* m = static_cast<plz4cu_membuf*>(ctx);
+    if (m->len + n > m->cap) return -1;
+    memcpy(m->data + m->len, data, n);
+    m->len += n;
+    return (int64_t)n;
+}
+int plz4cu_membuf_seek(void* ctx, int64_t delta)
+{
+    plz4cu_membuf* m = static_cast<plz4cu_membuf*>(ctx);
+    if (delta < 0 || m->pos + (size_t)delta > m->len) return -1;
+    m->pos += (size_t)delta;
+    return 0;
+}
 
 }  // extern "C"

@@ -19,6 +19,28 @@ vp = lambda a: C.c_void_p(a.ctypes.data)
 fn = lambda f: C.cast(f, C.c_void_p)
 res = {"host_cores": ncpu}
 
+from plz4_b200 import stream as S
+
+def c_compress(src_np, dst_np, **opts):
+    """NewWriter over in-memory C endpoints (no Python in the data path); returns the frame length."""
+    o, keep = S._opts(**opts)
+    sink = L.plz4cu_membuf_new(vp(dst_np), 0, dst_np.size)
+    w = L.plz4cu_writer_new(fn(L.plz4cu_membuf_write), sink, C.byref(o))
+    r = L.plz4cu_writer_write(w, vp(src_np), src_np.size); assert r == src_np.size, r
+    assert L.plz4cu_writer_close(w) == 0
+    n = L.plz4cu_membuf_len(sink)
+    L.plz4cu_writer_free(w); L.plz4cu_membuf_free(sink)
+    return n
+
+def c_decompress(frame_np, flen, dst_np, **opts):
+    o, keep = S._opts(**opts)
+    srcb = L.plz4cu_membuf_new(vp(frame_np), flen, flen)
+    sink = L.plz4cu_membuf_new(vp(dst_np), 0, dst_np.size)
+    r = L.plz4cu_reader_new(fn(L.plz4cu_membuf_read), fn(L.plz4cu_membuf_seek), srcb, C.byref(o))
+    n = L.plz4cu_reader_write_to(r, fn(L.plz4cu_membuf_write), sink); assert n >= 0, n
+    L.plz4cu_reader_close(r); L.plz4cu_reader_free(r); L.plz4cu_membuf_free(srcb); L.plz4cu_membuf_free(sink)
+    return n
+
 def logtext(n, seed=0x504C5A34):
     a = np.empty(n, dtype=np.uint8); L.plz4cu_gen_logtext_host(seed, 0, vp(a), n); return a
 
@@ -42,19 +64,24 @@ def cpu_blocks(data, bsz, checksum=1):
 # ---- configs[0]: 256 MiB log text, 4 MiB blocks, block + content checksums, host-resident streams
 data = logtext(256 << 20)
 raw = data.tobytes()
-def wr():
-    dst = io.BytesIO(); w = P.NewWriter(dst, block_size_idx=7, block_checksum=True, content_checksum=True, parallel=-1)
-    w.write(raw); w.close(); return dst.getvalue()
-frame = wr()
-def rd():
-    r = P.NewReader(io.BytesIO(frame), parallel=-1); out = io.BytesIO(); r.write_to(out); r.close(); return out.getvalue()
-assert rd() == raw
-tw, tr = best(lambda: wr(), 2), best(lambda: rd(), 2)
+fbuf = np.empty(data.size + (1 << 20), dtype=np.uint8); obuf = np.empty(data.size, dtype=np.uint8)
+o0 = dict(block_size_idx=7, block_checksum=True, content_checksum=True, parallel=-1)
+flen = c_compress(data, fbuf, **o0)
+assert c_decompress(fbuf, flen, obuf, parallel=-1) == data.size and obuf.tobytes() == raw
+tw = best(lambda: c_compress(data, fbuf, **o0), 2)
+tr = best(lambda: c_decompress(fbuf, flen, obuf, parallel=-1), 2)
+o0n = dict(o0, content_checksum=False)
+flen_n = c_compress(data, fbuf, **o0n)
+tw_n = best(lambda: c_compress(data, fbuf, **o0n), 2)
+tr_n = best(lambda: c_decompress(fbuf, flen_n, obuf, parallel=-1), 2)
+frame = bytes(flen)
 cc, cd, cr = cpu_blocks(data, 4 << 20)
 res["config0_256MiB_4MiB_blocks_bx_cx_streams"] = {
     "gpu_write_gbs": round(len(raw) / tw / 1e9, 2), "gpu_read_gbs": round(len(raw) / tr / 1e9, 2), "gpu_ratio": round(len(frame) / len(raw), 4),
+    "gpu_write_gbs_no_content_checksum": round(len(raw) / tw_n / 1e9, 2), "gpu_read_gbs_no_content_checksum": round(len(raw) / tr_n / 1e9, 2),
     "cpu_compress_gbs": round(cc, 2), "cpu_decompress_gbs": round(cd, 2), "cpu_ratio": round(cr, 4),
-    "note": "4 MiB blocks give 64 blocks = 64 warps: the GPU path is parallelism-starved here (DESIGN.md 6b)"}
+    "note": "NewWriter/NewReader over in-memory C endpoints, pageable caller buffers; CPU columns are block-level (no stream layer, no content checksum); "
+            "decode of 4 MiB blocks is one warp per block (64 blocks here): DESIGN.md 6b"}
 
 # ---- configs[2]: decode reference-produced frames (4 MiB blocks, bx) from random WithReadOffset starts
 from oracle import frame_oracle as F
@@ -63,10 +90,11 @@ marks = []
 rframe = F.write_frame(sub, F.Opts(block_idx=7, block_checksum=True, content_checksum=False), port, progress=lambda s, d: marks.append((s, d)))
 rng = np.random.default_rng(3)
 picks = [marks[i] for i in rng.integers(0, len(marks) - 1, size=4)]
+rf_np = np.frombuffer(rframe, dtype=np.uint8); ra_out = np.empty(len(sub), dtype=np.uint8)
 def ra():
     tot = 0
-    for s, d in picks:
-        r = P.NewReader(io.BytesIO(rframe), read_offset=d); tot += len(r.read_all()); r.close()
+    for s_, d_ in picks:
+        tot += c_decompress(rf_np, rf_np.size, ra_out, read_offset=d_)
     return tot
 tot = ra(); t3 = best(ra, 2)
 res["config2_random_access_reference_frames_4MiB"] = {"starts": len(picks), "decoded_bytes": tot, "gpu_gbs": round(tot / t3 / 1e9, 2)}
@@ -104,15 +132,19 @@ res["config3_4KiB_payloads_64KiB_dict"] = {
 seg = 1 << 20
 kinds = ["log", "log", "random", "zeros", "record1025", "log", "record1025", "log", "random", "log"]
 mixed = b"".join(make(kinds[i % 10], seg, seed=i) for i in range(256))
-def wr5():
-    dst = io.BytesIO(); w = P.NewWriter(dst, block_size_idx=5, block_checksum=True, content_checksum=True); w.write(mixed); w.close(); return dst.getvalue()
-f5 = wr5()
-def rd5():
-    r = P.NewReader(io.BytesIO(f5)); o = io.BytesIO(); r.write_to(o); r.close(); return o.getvalue()
-assert rd5() == mixed
-t5w, t5r = best(wr5, 2), best(rd5, 2)
+mixed_np = np.frombuffer(mixed, dtype=np.uint8)
+f5buf = np.empty(mixed_np.size + (1 << 20), dtype=np.uint8); o5buf = np.empty(mixed_np.size, dtype=np.uint8)
+o5 = dict(block_size_idx=5, block_checksum=True, content_checksum=True)
+f5len = c_compress(mixed_np, f5buf, **o5)
+assert c_decompress(f5buf, f5len, o5buf) == mixed_np.size and o5buf.tobytes() == mixed
+t5w = best(lambda: c_compress(mixed_np, f5buf, **o5), 2); t5r = best(lambda: c_decompress(f5buf, f5len, o5buf), 2)
+o5n = dict(o5, content_checksum=False)
+f5len_n = c_compress(mixed_np, f5buf, **o5n)
+t5w_n = best(lambda: c_compress(mixed_np, f5buf, **o5n), 2); t5r_n = best(lambda: c_decompress(f5buf, f5len_n, o5buf), 2)
+f5 = bytes(f5len)
 cc5, cd5, cr5 = cpu_blocks(np.frombuffer(mixed, dtype=np.uint8), 256 << 10)
 res["config4_mixed_256MiB_256KiB_blocks_bx_cx_streams"] = {
     "gpu_write_gbs": round(len(mixed) / t5w / 1e9, 2), "gpu_read_gbs": round(len(mixed) / t5r / 1e9, 2), "gpu_ratio": round(len(f5) / len(mixed), 4),
+    "gpu_write_gbs_no_content_checksum": round(len(mixed) / t5w_n / 1e9, 2), "gpu_read_gbs_no_content_checksum": round(len(mixed) / t5r_n / 1e9, 2),
     "cpu_compress_gbs": round(cc5, 2), "cpu_decompress_gbs": round(cd5, 2), "cpu_ratio": round(cr5, 4)}
 print(json.dumps(res, indent=1))
