@@ -316,6 +316,15 @@ def run_gpu(args) -> None:
             peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     except Exception:
         pass
+    # DRAM traffic per launch comes from an ncu --set full capture of this same workload (never measured in-run)
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        if int(t.get("bytes_per_gpu", 0)) == nbytes:
+            traffic = {k: v["traffic"] for k, v in t.items() if isinstance(v, dict) and "traffic" in v}
+    except Exception:
+        pass
     K = args.steps
     value = world * 2 * nbytes * K / tt_max / 1e9
     algo = nbytes + csize                       # per launch: U read + C' written (compress); C' read + U written (decompress)
@@ -329,10 +338,10 @@ def run_gpu(args) -> None:
         "decompress_gbs": round(world * nbytes * K / td_max / 1e9, 3),
         "compressed_ratio": round(csize / nbytes, 5),
         "roofline": {"bound": "hbm", "kernel": "lz4_compress_kernel", "achieved": round(c_ach, 2), "peak": peaks, "unit": "GB/s",
-                     "frac": round(c_ach / peaks, 5), "traffic": None, "peak_source": peak_src,
+                     "frac": round(c_ach / peaks, 5), "traffic": traffic.get("lz4_compress_kernel"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo, "launch_ms": round(tc / K * 1e3, 3)},
         "roofline_decompress": {"bound": "hbm", "kernel": "lz4_decompress_kernel", "achieved": round(d_ach, 2), "peak": peaks,
-                                "unit": "GB/s", "frac": round(d_ach / peaks, 5), "traffic": None,
+                                "unit": "GB/s", "frac": round(d_ach / peaks, 5), "traffic": traffic.get("lz4_decompress_kernel"),
                                 "algorithmic_bytes_per_launch": algo, "launch_ms": round(td / K * 1e3, 3)},
         "gpu_launches": int(launches), "clocks": clocks, "wall_s": round(t_wall, 3),
     }
