@@ -71,6 +71,39 @@ __device__ __noinline__ int emit_long(uint8_t* o, const uint8_t* __restrict__ li
     return w;
 }
 
+// Sequences chosen by the walk wait in a per-warp shared-memory queue as (literal start, literal count, match
+// length, offset) and are written 32 at a time, one sequence per lane: sizes are prefix-summed, each lane stores
+// its own token, length bytes, literals and offset.  Returns the bytes written, or -1 if they do not fit `room`.
+__device__ __noinline__ int flush_queue(const uint4* queue, int cnt, const uint8_t* __restrict__ src, uint8_t* out, int room, int lane)
+{
+    const bool mine = lane < cnt;
+    const uint4 e = mine ? queue[lane] : make_uint4(0, 0, MINMATCH, 0);
+    const int lit = (int)e.y, ml = (int)e.z - MINMATCH;
+    const int le = lit >= 15 ? ext_bytes(lit - 15) : 0;
+    const int me = ml >= 15 ? ext_bytes(ml - 15) : 0;
+    const int size = mine ? 1 + le + lit + 2 + me : 0;
+    int incl = size;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= d) incl += up;
+    }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    if (total > room) return -1;
+    if (mine) {
+        uint8_t* o = out + (incl - size);
+        *o++ = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (ml < 15 ? ml : 15));
+        if (le) { int r = lit - 15; for (; r >= 255; r -= 255) *o++ = 255; *o++ = (uint8_t)r; }
+        const uint8_t* lp = src + (int)e.x;
+        for (int j = 0; j < lit; j++) o[j] = lp[j];
+        o += lit;
+        o[0] = (uint8_t)e.w; o[1] = (uint8_t)(e.w >> 8);
+        o += 2;
+        if (me) { int r = ml - 15; for (; r >= 255; r -= 255) *o++ = 255; *o++ = (uint8_t)r; }
+    }
+    return total;
+}
+
 // kDict: the block may reference a read-only dictionary (a4: compress/indie.go:14-35, clz4.go:160-179).
 // Positions then live in a virtual space where the dictionary ends at 65536 and the block starts there;
 // the table starts as a copy of the dictionary's table instead of empty.
@@ -83,7 +116,7 @@ template <int kHashBits, bool kDict, bool kFrag>
 __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int n, uint8_t* dst,
                                             int cap, uint16_t* table, int lane,
                                             const uint8_t* __restrict__ dict, int dsz, const uint16_t* __restrict__ dict_table,
-                                            int prefix, uint32_t* tail_out)
+                                            int prefix, uint32_t* tail_out, uint4* queue)
 {
     constexpr uint32_t kEmpty = 0xFFFFu;
     constexpr int kProbe = 15;                       // bytes of every candidate examined in parallel
@@ -101,7 +134,7 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
     __syncwarp();
     constexpr int kVirt = kDict ? 65536 : 0;          // virtual position of block byte 0
 
-    int op = 0, anchor = 0;
+    int op = 0, anchor = 0, qn = 0;
     if (n >= MFLIMIT + 1) {
         const int mf_end = n - MFLIMIT + 1;          // a match may start at p < mf_end
         const int match_end = n - LASTLITERALS;      // and must end at or before match_end
@@ -253,71 +286,26 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             }
 
             if (starts) {
-                // ---- (b2) emit every chosen sequence of the group at once
+                // ---- (b2) queue the chosen sequences; they are written out 32 at a time by flush_queue()
                 const bool is_start = (starts >> lane) & 1u;
                 const uint32_t below = starts & ((1u << lane) - 1u);
                 const int g = 31 - __clz(below | 1u);
                 const int prev_end = __shfl_sync(FULL_MASK, lane + my_mlen, g);
                 const int P = below ? prev_end : (anchor - base);        // end of the previous match, lane units (may be < 0)
-                const int lit = lane - P;
-                const bool fits = !is_start || (lit < 15 && my_mlen < 19 + 255);
-                uint8_t* o = dst + op;
-                if (__all_sync(FULL_MASK, fits)) {
-                    const int xb = (my_mlen >= 19) ? 1 : 0;
-                    const int size = is_start ? (3 + lit + xb) : 0;
-                    int incl = size;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int up = __shfl_up_sync(FULL_MASK, incl, d);
-                        if (lane >= d) incl += up;
-                    }
-                    const int O = incl - size;
-                    const int T = __shfl_sync(FULL_MASK, incl, 31);
-                    if (op + T > cap) return 0;
-                    if (is_start) {
-                        const int ml = my_mlen - MINMATCH;
-                        uint8_t* os = o + O;
-                        os[0] = (uint8_t)((lit << 4) | (ml < 15 ? ml : 15));
-                        os += lit;
-                        os[1] = (uint8_t)my_off;
-                        os[2] = (uint8_t)(my_off >> 8);
-                        if (xb) os[3] = (uint8_t)(ml - 15);
-                    }
-                    // literal bytes of this group: uncovered lanes that have a chosen match above them
-                    const uint32_t atbelow = starts & ((2u << lane) - 1u);
-                    const int ps = 31 - __clz(atbelow | 1u);
-                    const int ps_len = __shfl_sync(FULL_MASK, my_mlen, ps);
-                    const bool covered = (atbelow && lane < ps + ps_len) || (lane < anchor - base);
-                    const uint32_t above = starts & ~((2u << lane) - 1u);
-                    const int ns = __ffs(above) - 1;
-                    const uint32_t where = __shfl_sync(FULL_MASK, (uint32_t)(O + 65 - P), ns);   // O + 1 - P, kept positive
-                    if (!covered && above) o[(int)where - 64 + lane] = (uint8_t)v_cur;
-                    // literals carried over from the previous group belong to the first sequence (O == 0)
-                    const int nc = base - anchor;
-                    if (nc > 0) {
-                        const uint32_t cb = __shfl_sync(FULL_MASK, v_prv, 32 - nc + lane);
-                        if (lane < nc) o[1 + lane] = (uint8_t)cb;
-                    }
-                    op += T;
-                } else {
-                    // rare: a literal run >= 15 or a match >= 274 in this group: one sequence at a time
-                    uint32_t st = starts;
-                    int a = anchor;
-                    while (st) {
-                        const int s = __ffs(st) - 1;
-                        st &= st - 1;
-                        const int mlen = __shfl_sync(FULL_MASK, my_mlen, s);
-                        const uint32_t off = __shfl_sync(FULL_MASK, my_off, s);
-                        const int mpos = base + s;
-                        const int l = mpos - a;
-                        const int mrest = mlen - MINMATCH - 15;
-                        const int need = 1 + (l >= 15 ? ext_bytes(l - 15) : 0) + l + 2 + (mrest >= 0 ? ext_bytes(mrest) : 0);
-                        if (op + need > cap) return 0;
-                        op += emit_long(dst + op, src + a, l, off, mlen, lane);
-                        a = mpos + mlen;
-                    }
-                }
+                if (is_start) queue[qn + __popc(below)] = make_uint4((uint32_t)(base + P), (uint32_t)(lane - P), (uint32_t)my_mlen, my_off);
+                qn += __popc(starts);
                 anchor = base + pos;
+                if (qn >= 32) {
+                    __syncwarp();
+                    const int w = flush_queue(queue, 32, src, dst + op, cap - op, lane);
+                    if (w < 0) return 0;
+                    op += w;
+                    const uint4 keep = queue[32 + lane];                 // slide the remainder down
+                    __syncwarp();
+                    queue[lane] = keep;
+                    qn -= 32;
+                    __syncwarp();
+                }
             }
             if (anchor >= base + kJumpAt) {
                 base = anchor;          // a long match skipped whole groups: their positions are not inserted
@@ -330,6 +318,12 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
                 v_nxt = v_far;
             }
         }
+    }
+    if (qn > 0) {
+        __syncwarp();
+        const int w = flush_queue(queue, qn, src, dst + op, cap - op, lane);
+        if (w < 0) return 0;
+        op += w;
     }
     if (kFrag) {
         *tail_out = (uint32_t)(n - anchor);          // the stitcher owns the final literal run
@@ -395,8 +389,9 @@ lz4_compress_kernel(EncodeArgs a)
     uint8_t* payload = a.raw_blocks ? rec : rec + 4;
     uint16_t* table = reinterpret_cast<uint16_t*>(smem + warp * kTableBytes);
 
+    __shared__ uint4 s_queue[kEncodeWarps][64];
     int c = encode_block<kHashBits, kDict, false>(src, n, payload, (int)a.dst_cap, table, lane, a.dict, (int)a.dict_size,
-                                                  a.dict_table, 0, nullptr);
+                                                  a.dict_table, 0, nullptr, s_queue[warp]);
     finish_record(a, b, src, n, rec, payload, c, lane);
 }
 
@@ -438,9 +433,10 @@ lz4_compress_frag_kernel(FragArgs a)
     const int n = min(kFragBytes, n_blk - start);
     const uint8_t* src = a.e.src_base + a.e.src_off[b] + start;
     uint16_t* table = reinterpret_cast<uint16_t*>(smem + warp * kTableBytes);
+    __shared__ uint4 s_queue[kEncodeWarps][64];
     uint32_t tail = 0;
     int c = encode_block<kHashBits, false, true>(src, n, a.tmp + (uint64_t)w * a.frag_stride, (int)a.frag_stride, table, lane,
-                                                 nullptr, 0, nullptr, start, &tail);
+                                                 nullptr, 0, nullptr, start, &tail, s_queue[warp]);
     if (lane == 0) { a.frag_len[w] = c; a.frag_tail[w] = tail; }
 }
 
