@@ -258,43 +258,33 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             // one word per lane for the walk: offset | length | flags
             const uint32_t pack = ((uint32_t)(p - cand) << 16) | ((uint32_t)eqlen << 8) | (lazy ? 4u : 0u) | (backok ? 2u : 0u) | (more ? 1u : 0u);
 
-            // ---- (b1) selection: registers only, except matches longer than kProbe
-            uint32_t starts = 0;                 // bit s: a chosen match starts at base+s
-            int my_mlen = 0;                     // on start lanes: final match length
-            uint32_t my_off = 0;                 //                 and offset
-            int pos = anchor > base ? anchor - base : 0;      // first lane not covered yet (may be >= 32)
-            uint32_t rem = (pos >= 32) ? 0u : (bal & (0xFFFFFFFFu << pos));
-            while (rem) {
-                int f = __ffs(rem) - 1;
-                uint32_t pk = __shfl_sync(FULL_MASK, pack, f);
-                if (pk & 4u) { f++; pk = __shfl_sync(FULL_MASK, pack, f) & ~2u; }
-                const uint32_t off = pk >> 16;
-                int mlen = (int)((pk >> 8) & 0xFFu);
-                if (pk & 1u) {
-                    const int a0 = base + f + kProbe, c0 = a0 - (int)off;      // c0 < 0: candidate bytes are in the dictionary
-                    const bool cd = kDict && c0 < 0;
-                    const uint8_t* cp = cd ? dict + (c0 + dsz) : src + c0;
-                    const int lim = cd ? min(match_end - a0, -c0) : match_end - a0;
-                    mlen += count_equal(src + a0, cp, lim, lane);
+            // ---- (b) walk the measured candidates (greedy, one-step lazy): registers only, except matches longer
+            // than kProbe.  Every chosen sequence goes into the shared-memory queue; flush_queue() writes them out.
+            {
+                int pos = anchor > base ? anchor - base : 0;      // first lane not covered yet (may be >= 32)
+                uint32_t rem = (pos >= 32) ? 0u : (bal & (0xFFFFFFFFu << pos));
+                while (rem) {
+                    int f = __ffs(rem) - 1;
+                    uint32_t pk = __shfl_sync(FULL_MASK, pack, f);
+                    if (pk & 4u) { f++; pk = __shfl_sync(FULL_MASK, pack, f) & ~2u; }
+                    const uint32_t off = pk >> 16;
+                    int mlen = (int)((pk >> 8) & 0xFFu);
+                    if (pk & 1u) {
+                        const int a0 = base + f + kProbe, c0 = a0 - (int)off;      // c0 < 0: candidate bytes are in the dictionary
+                        const bool cd = kDict && c0 < 0;
+                        const uint8_t* cp = cd ? dict + (c0 + dsz) : src + c0;
+                        const int lim = cd ? min(match_end - a0, -c0) : match_end - a0;
+                        mlen += count_equal(src + a0, cp, lim, lane);
+                    }
+                    const int s = ((pk & 2u) && f > pos) ? f - 1 : f;       // one byte backwards into the literals
+                    mlen += f - s;
+                    const int mpos = base + s;
+                    if (lane == 0) queue[qn] = make_uint4((uint32_t)anchor, (uint32_t)(mpos - anchor), (uint32_t)mlen, off);
+                    qn++;
+                    anchor = mpos + mlen;
+                    pos = s + mlen;
+                    rem = (pos >= 32) ? 0u : (rem & (0xFFFFFFFFu << pos));
                 }
-                const int s = ((pk & 2u) && f > pos) ? f - 1 : f;       // one byte backwards into the literals
-                mlen += f - s;
-                if (lane == s) { my_mlen = mlen; my_off = off; }
-                starts |= 1u << s;
-                pos = s + mlen;
-                rem = (pos >= 32) ? 0u : (rem & (0xFFFFFFFFu << pos));
-            }
-
-            if (starts) {
-                // ---- (b2) queue the chosen sequences; they are written out 32 at a time by flush_queue()
-                const bool is_start = (starts >> lane) & 1u;
-                const uint32_t below = starts & ((1u << lane) - 1u);
-                const int g = 31 - __clz(below | 1u);
-                const int prev_end = __shfl_sync(FULL_MASK, lane + my_mlen, g);
-                const int P = below ? prev_end : (anchor - base);        // end of the previous match, lane units (may be < 0)
-                if (is_start) queue[qn + __popc(below)] = make_uint4((uint32_t)(base + P), (uint32_t)(lane - P), (uint32_t)my_mlen, my_off);
-                qn += __popc(starts);
-                anchor = base + pos;
                 if (qn >= 32) {
                     __syncwarp();
                     const int w = flush_queue(queue, 32, src, dst + op, cap - op, lane);
