@@ -34,6 +34,14 @@ __constant__ int g_back_dev = 1;                // tuning knobs (see configure_c
 __constant__ int g_jump_dev = 64;
 __constant__ int g_lazy_dev = 1;                // 0 = greedy; k>0 = take p+1 if its match is longer by >= k
 
+// x << n with the hardware's semantics (a shift count >= 32 gives 0), which C leaves undefined
+__device__ __forceinline__ uint32_t shl_sat(uint32_t x, int n)
+{
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
+
 // bytes needed for the 255-run extension of a length whose nibble saturated
 __device__ __forceinline__ int ext_bytes(int rest) { return rest / 255 + 1; }
 
@@ -261,10 +269,10 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             // ---- (b) walk the measured candidates (greedy, one-step lazy): registers only, except matches longer
             // than kProbe.  Every chosen sequence goes into the shared-memory queue; flush_queue() writes them out.
             {
-                int pos = anchor > base ? anchor - base : 0;      // first lane not covered yet (may be >= 32)
-                uint32_t rem = (pos >= 32) ? 0u : (bal & (0xFFFFFFFFu << pos));
+                int pos = max(anchor - base, 0);                  // first lane not covered yet (may be >= 32)
+                uint32_t rem = bal & shl_sat(0xFFFFFFFFu, pos);
                 while (rem) {
-                    int f = __ffs(rem) - 1;
+                    int f = __clz(__brev(rem));
                     uint32_t pk = __shfl_sync(FULL_MASK, pack, f);
                     if (pk & 4u) { f++; pk = __shfl_sync(FULL_MASK, pack, f) & ~2u; }
                     const uint32_t off = pk >> 16;
@@ -276,14 +284,14 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
                         const int lim = cd ? min(match_end - a0, -c0) : match_end - a0;
                         mlen += count_equal(src + a0, cp, lim, lane);
                     }
-                    const int s = ((pk & 2u) && f > pos) ? f - 1 : f;       // one byte backwards into the literals
-                    mlen += f - s;
-                    const int mpos = base + s;
+                    const int back = (int)((pk >> 1) & 1u) & (int)(f > pos);        // one byte backwards into the literals
+                    mlen += back;
+                    const int mpos = base + f - back;
                     if (lane == 0) queue[qn] = make_uint4((uint32_t)anchor, (uint32_t)(mpos - anchor), (uint32_t)mlen, off);
                     qn++;
                     anchor = mpos + mlen;
-                    pos = s + mlen;
-                    rem = (pos >= 32) ? 0u : (rem & (0xFFFFFFFFu << pos));
+                    pos = anchor - base;
+                    rem &= shl_sat(0xFFFFFFFFu, pos);
                 }
                 if (qn >= 32) {
                     __syncwarp();
