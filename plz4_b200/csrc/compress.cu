@@ -14,9 +14,9 @@
 //       neighbours' registers by shuffle — giving a match length of up to 15, a backward byte and a
 //       one-step-lazy hint, then
 //   (b) walks the measured candidates with no memory access on the common path (only matches longer
-//       than 15 go back to memory), and emits ALL sequences of the group at once: sizes are
-//       prefix-summed across lanes, match-start lanes store token / offset / length byte, literal
-//       lanes store their own byte.
+//       than 15 go back to memory) and appends every chosen sequence to a shared-memory queue;
+//       every 32 sequences the queue is written out one sequence per lane (sizes prefix-summed,
+//       each lane stores its own token, length bytes, literals and offset).
 // The table holds the low 16 bits of positions: LZ4's window is 64 KiB, so that is enough for any
 // block size (a stale entry aliases into the window and is caught by the byte comparison).
 // The output is a valid LZ4 block obeying the end-of-block rules liblz4's decoder enforces
@@ -62,21 +62,6 @@ __device__ __noinline__ int count_equal(const uint8_t* __restrict__ a, const uin
         if (ne) return total + (__ffs(ne) - 1);
         total += 32;
     }
-}
-
-// General (rare) sequence emit: literal run >= 15 or match >= 274.
-__device__ __noinline__ int emit_long(uint8_t* o, const uint8_t* __restrict__ lits, int lit, uint32_t off, int mlen, int lane)
-{
-    const int mrest = mlen - MINMATCH - 15;
-    if (lane == 0) o[0] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mrest >= 0 ? 15 : mlen - MINMATCH));
-    int w = 1;
-    if (lit >= 15) { put_ext(o + w, lit - 15, lane); w += ext_bytes(lit - 15); }
-    warp_copy(o + w, lits, (uint32_t)lit, lane);
-    w += lit;
-    if (lane == 0) { o[w] = (uint8_t)off; o[w + 1] = (uint8_t)(off >> 8); }
-    w += 2;
-    if (mrest >= 0) { put_ext(o + w, mrest, lane); w += ext_bytes(mrest); }
-    return w;
 }
 
 // Sequences chosen by the walk wait in a per-warp shared-memory queue as (literal start, literal count, match
