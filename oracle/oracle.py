@@ -186,6 +186,25 @@ class Ref:
     def dict_create(self, d) -> "RefDict":
         return RefDict(self, d)
 
+    def xxh32(self, data) -> int:
+        """The reference's xxh32 is Go; the pinned port (== python-xxhash, tests/test_oracle_vs_ref.py) stands in."""
+        if not hasattr(self, "_port"):
+            self._port = Port()
+        return self._port.xxh32(data)
+
+    def block_record(self, src, bsz: int, checksum: bool, dict_: "RefDict | None" = None) -> bytes:
+        """blk.CompressToBlk (blk/blk.go:69-109) on top of the reference's liblz4."""
+        src = bytes(src)
+        c = dict_.compress(src, bsz) if dict_ else self.compress(src, bsz)
+        if c is None:
+            c, word = src, len(src) | 0x80000000
+        else:
+            word = len(c)
+        rec = word.to_bytes(4, "little") + c
+        if checksum:
+            rec += self.xxh32(c).to_bytes(4, "little")
+        return rec
+
 
 class RefDict:
     """clz4.go:96-120 NewDictCtx + :151-179 StreamIndieCtx (fresh working ctx per call)."""
