@@ -369,7 +369,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="plz4_b200", choices=["plz4_b200", "reference"])
     ap.add_argument("--gib", type=float, default=8.0, help="uncompressed GiB per GPU (configs[1] = 8)")
-    ap.add_argument("--e2e-gib", type=float, default=4.0, help="GiB per GPU pushed through the host-buffer API per step")
+    ap.add_argument("--e2e-gib", type=float, default=8.0, help="GiB per GPU pushed through the host-buffer API per step")
     ap.add_argument("--cpu-sample-mib", type=int, default=2048, help="bounded sample for the CPU baseline / reference arm")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

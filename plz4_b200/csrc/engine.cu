@@ -1,7 +1,7 @@
 // engine.cu — the C ABI declared in include/plz4cu.h.
 //
 // Device-resident entry points are thin launches on the caller's stream.  Host-resident entry
-// points stage through a per-device pipeline context (grow-only device scratch, two lanes of
+// points lease a pipeline context of their device (grow-only device scratch, kLanes lanes of
 // stream + buffers) so that H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 overlap.
 // There is NO CPU codec in this library: without a usable GPU every entry point fails loudly.
 #include "../../include/plz4cu.h"
@@ -9,6 +9,7 @@
 #include "logtext.h"
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -123,11 +124,7 @@ struct Lane {
     HostBuf h_meta, h_res;      // pinned staging for small metadata (up / down)
 };
 
-
-
 struct Pipe {
-    std::mutex mu;
-    int device = -1;
     Lane lane[kMaxLanes];
     bool ready = false;
     int init()
@@ -142,17 +139,49 @@ struct Pipe {
     }
 };
 
-std::mutex g_pipes_mu;
-std::vector<Pipe*> g_pipes;
-Pipe* pipe_for_current_device()
-{
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    std::lock_guard<std::mutex> lk(g_pipes_mu);
-    if ((int)g_pipes.size() <= dev) g_pipes.resize(dev + 1, nullptr);
-    if (!g_pipes[dev]) { g_pipes[dev] = new Pipe(); g_pipes[dev]->device = dev; }
-    return g_pipes[dev];
-}
+// Host-resident calls from different threads (many writers / readers, the reference's one-goroutine-per-stream use)
+// each lease a whole pipe, so their copies and kernels overlap on the device; up to kMaxPipes per device, further
+// callers queue for a free one.
+constexpr int kMaxPipes = 4;
+struct PipePool {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Pipe*> idle;
+    int created = 0;
+};
+std::mutex g_pools_mu;
+std::vector<PipePool*> g_pools;
+
+class PipeLease {
+    PipePool* pool = nullptr;
+    Pipe* pipe = nullptr;
+public:
+    PipeLease()
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return;
+        {
+            std::lock_guard<std::mutex> lk(g_pools_mu);
+            if ((int)g_pools.size() <= dev) g_pools.resize(dev + 1, nullptr);
+            if (!g_pools[dev]) g_pools[dev] = new PipePool();
+            pool = g_pools[dev];
+        }
+        std::unique_lock<std::mutex> lk(pool->mu);
+        if (pool->idle.empty() && pool->created < kMaxPipes) { pool->created++; pipe = new Pipe(); return; }
+        pool->cv.wait(lk, [&] { return !pool->idle.empty(); });
+        pipe = pool->idle.back();
+        pool->idle.pop_back();
+    }
+    ~PipeLease()
+    {
+        if (!pipe) return;
+        { std::lock_guard<std::mutex> lk(pool->mu); pool->idle.push_back(pipe); }
+        pool->cv.notify_one();
+    }
+    PipeLease(const PipeLease&) = delete;
+    PipeLease& operator=(const PipeLease&) = delete;
+    Pipe* get() const { return pipe; }
+};
 
 inline uint32_t round_up16(uint32_t v) { return (v + 15u) & ~15u; }
 
@@ -394,7 +423,6 @@ int plz4cu_gen_logtext_host(uint32_t seed, uint64_t first_seg, void* dst, uint64
 // All small metadata crosses PCIe through pinned staging, so no call in the loop blocks the host
 // except the explicit waits.
 
-
 namespace {
 struct Chunk { uint32_t b0, b1; uint64_t lo, hi; };     // blocks [b0,b1), input byte span [lo,hi)
 }
@@ -408,9 +436,9 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
     packed_off[0] = 0;
     if (nblk == 0) return 0;
     if (!src || !src_off || !src_len || !packed) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: null pointer");
-    Pipe* pp = pipe_for_current_device();
+    PipeLease lease;
+    Pipe* pp = lease.get();
     if (!pp) return fail(PLZ4CU_ERR_NODEVICE, "no CUDA device");
-    std::lock_guard<std::mutex> lk(pp->mu);
     if (int r = pp->init()) return r;
 
     const uint8_t* hsrc = static_cast<const uint8_t*>(src);
@@ -506,9 +534,9 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
     if (!recs || !rec_off || !dst || !out_len) return fail(PLZ4CU_ERR_ARG, "decompress_batch_host: null pointer");
     if (raw_blocks && !raw_len) return fail(PLZ4CU_ERR_ARG, "decompress_batch_host: raw_len required for raw blocks");
     if (dst_stride < dst_cap) return fail(PLZ4CU_ERR_ARG, "decompress_batch_host: dst_stride < dst_cap");
-    Pipe* pp = pipe_for_current_device();
+    PipeLease lease;
+    Pipe* pp = lease.get();
     if (!pp) return fail(PLZ4CU_ERR_NODEVICE, "no CUDA device");
-    std::lock_guard<std::mutex> lk(pp->mu);
     if (int r = pp->init()) return r;
 
     const uint8_t* hrec = static_cast<const uint8_t*>(recs);

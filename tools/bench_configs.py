@@ -131,7 +131,7 @@ res["config3_4KiB_payloads_64KiB_dict"] = {
 # ---- configs[4] in miniature: mixed-entropy stream, 256 KiB blocks, block + content checksum, NewWriter / NewReader
 seg = 1 << 20
 kinds = ["log", "log", "random", "zeros", "record1025", "log", "record1025", "log", "random", "log"]
-mixed = b"".join(make(kinds[i % 10], seg, seed=i) for i in range(256))
+mixed = b"".join(make(kinds[i % 10], seg, seed=i) for i in range(256)) * 4          # 1 GiB: 256 distinct MiB, four times
 mixed_np = np.frombuffer(mixed, dtype=np.uint8)
 f5buf = np.empty(mixed_np.size + (1 << 20), dtype=np.uint8); o5buf = np.empty(mixed_np.size, dtype=np.uint8)
 o5 = dict(block_size_idx=5, block_checksum=True, content_checksum=True)
@@ -143,8 +143,17 @@ f5len_n = c_compress(mixed_np, f5buf, **o5n)
 t5w_n = best(lambda: c_compress(mixed_np, f5buf, **o5n), 2); t5r_n = best(lambda: c_decompress(f5buf, f5len_n, o5buf), 2)
 f5 = bytes(f5len)
 cc5, cd5, cr5 = cpu_blocks(np.frombuffer(mixed, dtype=np.uint8), 256 << 10)
-res["config4_mixed_256MiB_256KiB_blocks_bx_cx_streams"] = {
+res["config4_mixed_1GiB_256KiB_blocks_bx_cx_streams"] = {
     "gpu_write_gbs": round(len(mixed) / t5w / 1e9, 2), "gpu_read_gbs": round(len(mixed) / t5r / 1e9, 2), "gpu_ratio": round(len(f5) / len(mixed), 4),
     "gpu_write_gbs_no_content_checksum": round(len(mixed) / t5w_n / 1e9, 2), "gpu_read_gbs_no_content_checksum": round(len(mixed) / t5r_n / 1e9, 2),
     "cpu_compress_gbs": round(cc5, 2), "cpu_decompress_gbs": round(cd5, 2), "cpu_ratio": round(cr5, 4)}
+
+# ---- what one host thread can do on this box: the ceilings of any stream layer that copies caller bytes once
+# (staging in, result out) and hashes the content serially
+big = mixed_np[: 256 << 20]; tmp = np.empty_like(big)
+L.plz4cu_xxh32_host.restype = C.c_uint32
+res["host_single_thread_bounds"] = {
+    "memcpy_gbs": round(big.size / best(lambda: np.copyto(tmp, big)) / 1e9, 2),
+    "xxh32_gbs": round(big.size / best(lambda: L.plz4cu_xxh32_host(vp(big), big.size)) / 1e9, 2),
+    "note": "content checksum (xxh32 of the uncompressed stream) is serial by definition: streams with it cannot exceed xxh32_gbs"}
 print(json.dumps(res, indent=1))
