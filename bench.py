@@ -261,7 +261,9 @@ def run_gpu(args) -> None:
     # ---- e2e through the host-buffer C ABI (pinned host memory; H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
-        e_bytes = min(nbytes, int(args.e2e_gib * (1 << 30)) // BSZ * BSZ)
+        # three pinned buffers per rank: keep the box-wide total bounded (16 GiB of input across all ranks)
+        e_gib = args.e2e_gib if world <= 2 else min(args.e2e_gib, 16.0 / world)
+        e_bytes = min(nbytes, int(e_gib * (1 << 30)) // BSZ * BSZ)
         e_blk = e_bytes // BSZ
         h_src = torch.empty(e_bytes, dtype=torch.uint8).pin_memory()
         h_src.copy_(src[:e_bytes])

@@ -193,6 +193,17 @@ PLZ4CU_API int plz4cu_xxh32_batch_device(plz4cu_stream_t stream, const void* bas
  *   write: return bytes written (== n) or a negative value to signal an I/O error
  *   read : return bytes read (short reads allowed), 0 at end of stream, negative on I/O error
  *   seek : optional (may be NULL): skip `delta` bytes forward; return 0, or negative if it cannot seek
+ *
+ * Threading (mirrors the reference's sync / async packages, opts.NParallel): with n_parallel == 0 everything,
+ * callbacks included, runs on the calling thread, one block per engine call.  With n_parallel != 0 the stream is
+ * staged over helper threads it owns: a writer's sink and progress callbacks are invoked from one internal thread,
+ * in block order, and an I/O or engine error surfaces on a later Write / Flush / Close, once (async/writer.go:
+ * 175-190); a reader's source callback is invoked from one internal thread that reads and decodes one batch ahead.
+ * Callbacks of one stream never run concurrently with each other; a writer's have all returned when Flush / Close
+ * return, a reader's source callback may run between Read calls (read-ahead) and never after Close returned.
+ * A stream object itself is not thread-safe (one caller at a time, as in the reference); distinct streams are
+ * independent and may be used from different threads.  A writer starts its helper threads only once the stream
+ * outgrows 8 MiB; until then (and for every small stream) it behaves like the synchronous flavour.
  */
 typedef int64_t (*plz4cu_write_fn)(void* ctx, const void* data, size_t n);
 typedef int64_t (*plz4cu_read_fn)(void* ctx, void* buf, size_t n);
@@ -206,8 +217,9 @@ typedef int     (*plz4cu_dict_fn)(void* ctx, uint32_t dict_id, const void** dict
 
 typedef struct plz4cu_opts {
     int32_t  level;              /* WithLevel: only 1 is implemented by this engine                       */
-    int32_t  n_parallel;         /* WithParallel: 0 = one block per engine call; != 0 = batched            */
-    int32_t  pending_size;       /* WithPendingSize: bytes of blocks batched per engine call (-1/0 = auto) */
+    int32_t  n_parallel;         /* WithParallel: 0 = synchronous, one block per engine call; != 0 = staged */
+    int32_t  pending_size;       /* WithPendingSize: bytes of blocks per engine call (<= 0: auto, 64 MiB;   */
+                                 /*   readers of >= 1 MiB blocks: 256 MiB)                                  */
     int32_t  block_size_idx;     /* WithBlockSize: 4..7 (64 KiB, 256 KiB, 1 MiB, 4 MiB)                    */
     int32_t  block_checksum;     /* WithBlockChecksum                                                      */
     int32_t  content_checksum;   /* WithContentChecksum                                                    */

@@ -304,6 +304,7 @@ struct plz4cu_writer {
     int bsz;
     size_t batch;
     const bool async;                                 // n_parallel != 0: stage, engine + sink, content hash overlap
+    bool threaded = false;                            // ... from the moment the stream proves large (first slab)
     const int device;
     bool header_written = false, closed = false, reported = false;
     std::atomic<int> state{0};                        // sticky error (first error wins, async/writer.go:553-555)
@@ -377,12 +378,12 @@ struct plz4cu_writer {
         const size_t packed_cap = (size_t)nblk * (bsz + 8);
         Packed& pk = packed[pk_cur];
         pk_cur ^= 1;
-        if (async) sink_q.wait(pk.sink_ticket);
+        if (threaded) sink_q.wait(pk.sink_ticket);
         if (!pk.buf.reserve(packed_cap)) return PLZ4CU_Z_ENGINE;
         int rc = plz4cu_compress_batch_host(data, offs.data(), lens.data(), nblk, (uint32_t)bsz, opt.o.block_checksum, 0, dict,
                                             pk.buf.p, packed_cap, poff.data());
         if (rc < 0) return PLZ4CU_Z_ENGINE;
-        if (!async) return deliver(pk.buf.p, n, lens, poff);
+        if (!threaded) return deliver(pk.buf.p, n, lens, poff);
         // the sink job owns copies of the per-block tables only when somebody watches block boundaries
         std::vector<uint32_t> jl;
         std::vector<uint64_t> jp;
@@ -420,10 +421,14 @@ struct plz4cu_writer {
     void dispatch(const uint8_t* data, size_t n, Slab* slab)
     {
         if (n == 0) return;
-        if (!async) {
-            // synchronous flavour (sync/writer.go:53-290): the content checksum still runs beside the GPU
+        if (!threaded) {
+            // synchronous flavour (sync/writer.go:53-290), and the first bytes of any stream: everything on the
+            // caller's thread; only a large batch is worth a helper for the content checksum
             std::future<void> hf;
-            if (opt.o.content_checksum) hf = std::async(std::launch::async, [=] { hasher.update(data, n); });
+            if (opt.o.content_checksum) {
+                if (n >= (1u << 20)) hf = std::async(std::launch::async, [=] { hasher.update(data, n); });
+                else hasher.update(data, n);
+            }
             int e = emit(data, n);
             if (hf.valid()) hf.get();
             if (e) set_error(e);
@@ -457,6 +462,7 @@ struct plz4cu_writer {
         }
         slabs[0].p = static_cast<uint8_t*>(plz4cu_host_alloc(batch));
         if (!slabs[0].p) return false;
+        threaded = true;                               // the stream is large: from here on the stages overlap
         memcpy(slabs[0].p, small.data(), fill);
         small.clear(); small.shrink_to_fit();
         cur_slab = 0;
@@ -498,6 +504,7 @@ struct plz4cu_writer {
                 // whole batches straight from the caller's buffer, no staging copy (sync/writer.go:99-109); when
                 // batching this is only a win for page-locked memory — pageable bytes are staged so that the copy
                 // overlaps the GPU instead of crawling over PCIe through the driver's bounce buffer
+                if (async) threaded = true;
                 dispatch(src + done, batch, nullptr);
                 done += batch;
                 continue;
@@ -803,26 +810,40 @@ struct plz4cu_reader {
                 for (uint32_t i = 0; i < b.nblk && b.out_len[i] >= 0; i++) hasher.update(b.out.p + (size_t)i * bsz, (size_t)b.out_len[i]);
                 b.digest = hasher.digest();
             };
-            if (async) b.hash_ticket = hash_q.submit(job); else job();
+            // small batches are hashed in place (in order: the hash thread, if it ever started, is idle first)
+            if (async && (size_t)b.nblk * bsz >= (1u << 20)) b.hash_ticket = hash_q.submit(job);
+            else { hash_q.drain(); job(); }
         }
     }
-    void start_fill(Batch& b)
+    size_t next_fill_bytes()
     {
+        const size_t limit = opt.batch_bytes(bsz, true);
+        if (!async) return limit;
         // first batch: 64 blocks (a batch costs at least one block's decode time, so large blocks start large)
         if (next_batch_bytes == 0) next_batch_bytes = std::max<size_t>(64 * (size_t)bsz, 1u << 20);
-        const size_t want = std::min(next_batch_bytes, opt.batch_bytes(bsz, true));
-        next_batch_bytes = std::min(opt.batch_bytes(bsz, true), next_batch_bytes * 4);
-        if (!async) { fill_batch(b, opt.batch_bytes(bsz, true)); return; }
-        b.ticket = engine_q.submit([this, &b, want] { cudaSetDevice(device); fill_batch(b, want); });
+        const size_t want = std::min(next_batch_bytes, limit);
+        next_batch_bytes = std::min(limit, next_batch_bytes * 4);
+        return want;
     }
-    // make the next batch current; keeps one more in flight while the frame body goes on
+    // make the next batch current; while the frame body goes on, one more is read and decoded ahead on the engine
+    // thread.  The first batch of a body is filled on the caller's thread (it is waited for anyway), so a stream
+    // that fits one batch never starts a thread.
     void advance_batch()
     {
-        if (prefetched) { cb ^= 1; prefetched = false; }
-        else start_fill(bt[cb]);
-        if (async) engine_q.wait(bt[cb].ticket);
+        if (prefetched) {
+            cb ^= 1;
+            prefetched = false;
+            engine_q.wait(bt[cb].ticket);
+        } else {
+            fill_batch(bt[cb], next_fill_bytes());
+        }
         cur = 0;
-        if (async && bt[cb].tail_event == 0 && bt[cb].nblk > 0) { start_fill(bt[cb ^ 1]); prefetched = true; }
+        if (async && bt[cb].tail_event == 0 && bt[cb].nblk > 0) {
+            Batch& nb = bt[cb ^ 1];
+            const size_t want = next_fill_bytes();
+            nb.ticket = engine_q.submit([this, &nb, want] { cudaSetDevice(device); fill_batch(nb, want); });
+            prefetched = true;
+        }
     }
 
     // rdr/rdr.go:207-227 nextBlock: 0 = a block is current, 2 = EndMark, <0 error
@@ -861,7 +882,7 @@ struct plz4cu_reader {
         if (ev == 2) {
             src_pos += b.endmark_read;
             if (verify_content_hash) {
-                if (async) hash_q.wait(b.hash_ticket);
+                hash_q.wait(b.hash_ticket);
                 if (b.digest != b.content_hash_read) return PLZ4CU_Z_CONTENT_HASH;
             }
             return 2;
