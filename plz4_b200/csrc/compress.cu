@@ -30,6 +30,17 @@
 namespace plz4 {
 
 constexpr int kEncodeWarps = 4;                 // blocks per CTA
+constexpr int kQueueLen = 48;                   // sequences queued per warp: 32 to flush + the <= 8 a group can add
+
+// Table geometry.  The 12-bit table uses 7/8 of its 4096 slots: 3584 x u16 = 7 KiB per warp, which lets a seventh
+// CTA (28 warps instead of 24) fit an SM's 227 KiB of shared memory next to the sequence queues.
+__host__ __device__ constexpr int table_slots(int bits) { return bits == 12 ? 3584 : (1 << bits); }
+__host__ __device__ constexpr int table_bytes(int bits) { return 2 * table_slots(bits); }
+__host__ __device__ __forceinline__ uint32_t table_slot(uint32_t v, int bits)
+{
+    const uint32_t h = (v * 2654435761u) >> (32 - bits);       // liblz4's hash4 (lz4.c:777-783)
+    return bits == 12 ? (h * 7u) >> 3 : h;
+}
 __constant__ int g_back_dev = 1;                // tuning knobs (see configure_compress)
 __constant__ int g_jump_dev = 64;
 __constant__ int g_lazy_dev = 1;                // 0 = greedy; k>0 = take p+1 if its match is longer by >= k
@@ -121,7 +132,7 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
         uint4 fill = make_uint4(~0u, ~0u, ~0u, ~0u);
         uint4* t4 = reinterpret_cast<uint4*>(table);
         const uint4* d4 = reinterpret_cast<const uint4*>(dict_table);
-        constexpr int kVecs = (2 << kHashBits) / 16;
+        constexpr int kVecs = table_bytes(kHashBits) / 16;
         for (int i = lane; i < kVecs; i += 32) t4[i] = kDict ? d4[i] : fill;
     }
     __syncwarp();
@@ -149,7 +160,7 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             constexpr int kPrewarm = 16384;
             for (int q0 = -min(prefix, kPrewarm); q0 < 0; q0 += 32) {
                 const int q = q0 + lane;
-                const uint32_t hv = (own4(q) * 2654435761u) >> (32 - kHashBits);
+                const uint32_t hv = table_slot(own4(q), kHashBits);
                 const uint32_t same = __match_any_sync(FULL_MASK, hv);
                 if ((same >> lane) == 1u) table[hv] = (uint16_t)q;
             }
@@ -174,7 +185,7 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             uint32_t h = 0x80000000u | (uint32_t)lane;
             int cand = -0x40000000;                               // "none": fails the distance test below
             if (valid) {
-                h = (v * 2654435761u) >> (32 - kHashBits);
+                h = table_slot(v, kHashBits);
                 const uint32_t c = table[h];
                 const int vp = p + kVirt;
                 int q = (int)(((uint32_t)vp & 0xFFFF0000u) | c);
@@ -283,9 +294,9 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
                     const int w = flush_queue(queue, 32, src, dst + op, cap - op, lane);
                     if (w < 0) return 0;
                     op += w;
-                    const uint4 keep = queue[32 + lane];                 // slide the remainder down
+                    const uint4 keep = queue[32 + (lane & (kQueueLen - 32 - 1))];    // slide the remainder (< 16) down
                     __syncwarp();
-                    queue[lane] = keep;
+                    if (lane < kQueueLen - 32) queue[lane] = keep;
                     qn -= 32;
                     __syncwarp();
                 }
@@ -356,11 +367,11 @@ __device__ __forceinline__ void finish_record(const EncodeArgs& a, uint32_t b, c
 }
 
 template <int kHashBits, bool kDict>
-__global__ void __launch_bounds__(kEncodeWarps * 32, 6)
+__global__ void __launch_bounds__(kEncodeWarps * 32, 7)
 lz4_compress_kernel(EncodeArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kTableBytes = 2 << kHashBits;      // u16[1 << bits]
+    constexpr int kTableBytes = table_bytes(kHashBits);
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const uint32_t b = blockIdx.x * kEncodeWarps + warp;
@@ -372,7 +383,7 @@ lz4_compress_kernel(EncodeArgs a)
     uint8_t* payload = a.raw_blocks ? rec : rec + 4;
     uint16_t* table = reinterpret_cast<uint16_t*>(smem + warp * kTableBytes);
 
-    __shared__ uint4 s_queue[kEncodeWarps][64];
+    __shared__ uint4 s_queue[kEncodeWarps][kQueueLen];
     int c = encode_block<kHashBits, kDict, false>(src, n, payload, (int)a.dst_cap, table, lane, a.dict, (int)a.dict_size,
                                                   a.dict_table, 0, nullptr, s_queue[warp]);
     finish_record(a, b, src, n, rec, payload, c, lane);
@@ -397,11 +408,11 @@ struct FragArgs {
 };
 
 template <int kHashBits>
-__global__ void __launch_bounds__(kEncodeWarps * 32, 6)
+__global__ void __launch_bounds__(kEncodeWarps * 32, 7)
 lz4_compress_frag_kernel(FragArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kTableBytes = 2 << kHashBits;
+    constexpr int kTableBytes = table_bytes(kHashBits);
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const uint32_t w = blockIdx.x * kEncodeWarps + warp;
@@ -416,7 +427,7 @@ lz4_compress_frag_kernel(FragArgs a)
     const int n = min(kFragBytes, n_blk - start);
     const uint8_t* src = a.e.src_base + a.e.src_off[b] + start;
     uint16_t* table = reinterpret_cast<uint16_t*>(smem + warp * kTableBytes);
-    __shared__ uint4 s_queue[kEncodeWarps][64];
+    __shared__ uint4 s_queue[kEncodeWarps][kQueueLen];
     uint32_t tail = 0;
     int c = encode_block<kHashBits, false, true>(src, n, a.tmp + (uint64_t)w * a.frag_stride, (int)a.frag_stride, table, lane,
                                                  nullptr, 0, nullptr, start, &tail, s_queue[warp]);
@@ -521,7 +532,7 @@ __global__ void __launch_bounds__(1024) dict_table_kernel(const uint8_t* __restr
     __syncthreads();
     for (int j = threadIdx.x; j + 4 <= dsz; j += blockDim.x) {
         const uint32_t v = (uint32_t)dict[j] | ((uint32_t)dict[j + 1] << 8) | ((uint32_t)dict[j + 2] << 16) | ((uint32_t)dict[j + 3] << 24);
-        atomicMax(&best[(v * 2654435761u) >> (32 - bits)], j);
+        atomicMax(&best[table_slot(v, bits)], j);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < entries; i += blockDim.x)
@@ -534,20 +545,20 @@ cudaError_t launch_dict_build(const uint8_t* dict, uint32_t dict_size, int bits,
     return cudaGetLastError();
 }
 
-static int g_hash_bits = 12;     // 8 KiB of table per warp: twice the resident warps of liblz4's 13 bits; the one-step
-                                 // lazy parse more than pays the ratio back (profiles/r01_sweep.txt)
+static int g_hash_bits = 12;     // 7 KiB of table per warp: 28 resident warps per SM against 12 with liblz4's 13 bits;
+                                 // the one-step lazy parse more than pays the ratio back (profiles/r01_sweep.txt)
 
 template <int kBits>
 static cudaError_t set_smem_attr()
 {
     cudaError_t e = cudaFuncSetAttribute(lz4_compress_kernel<kBits, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kEncodeWarps * (2 << kBits));
+                                         kEncodeWarps * table_bytes(kBits));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lz4_compress_kernel<kBits, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kEncodeWarps * (2 << kBits));
+                             kEncodeWarps * table_bytes(kBits));
     if (e != cudaSuccess || kBits == 13) return e;
     return cudaFuncSetAttribute(lz4_compress_frag_kernel<(kBits == 13 ? 12 : kBits)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kEncodeWarps * (2 << kBits));
+                                kEncodeWarps * table_bytes(kBits));
 }
 
 int compress_hash_bits(uint32_t dst_cap)
@@ -598,7 +609,7 @@ cudaError_t configure_compress()
 template <int kBits>
 static cudaError_t launch_frag(const FragArgs& fa, uint32_t nwarps, cudaStream_t stream)
 {
-    lz4_compress_frag_kernel<kBits><<<(nwarps + kEncodeWarps - 1) / kEncodeWarps, kEncodeWarps * 32, kEncodeWarps * (2 << kBits), stream>>>(fa);
+    lz4_compress_frag_kernel<kBits><<<(nwarps + kEncodeWarps - 1) / kEncodeWarps, kEncodeWarps * 32, kEncodeWarps * table_bytes(kBits), stream>>>(fa);
     return cudaGetLastError();
 }
 
@@ -631,7 +642,7 @@ cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
     }
     dim3 grid((a.nblk + kEncodeWarps - 1) / kEncodeWarps), block(kEncodeWarps * 32);
     const int bits = compress_hash_bits(a.dst_cap);
-    const size_t sm = (size_t)kEncodeWarps * (2u << bits);
+    const size_t sm = (size_t)kEncodeWarps * table_bytes(bits);
     const bool d = a.dict_size > 0;
     if (bits == 11)      { if (d) lz4_compress_kernel<11, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<11, false><<<grid, block, sm, stream>>>(a); }
     else if (bits == 12) { if (d) lz4_compress_kernel<12, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<12, false><<<grid, block, sm, stream>>>(a); }
