@@ -62,16 +62,21 @@ __device__ __forceinline__ void put_ext(uint8_t* o, int rest, int lane)
     for (int k = lane; k < nb; k += 32) o[k] = (k == nb - 1) ? (uint8_t)(rest - 255 * (nb - 1)) : (uint8_t)255;
 }
 
-// Long-match tail: number of equal bytes of a[0..] and b[0..], at most `limit`, 32 per ballot.
+// Long-match tail: number of equal bytes of a[0..] and b[0..], at most `limit`.  64 bytes per round, all four loads in
+// flight before the first ballot.
 __device__ __noinline__ int count_equal(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int limit, int lane)
 {
     int total = 0;
     for (;;) {
-        int k = total + lane;
-        bool eq = (k < limit) && (a[k] == b[k]);
-        uint32_t ne = __ballot_sync(FULL_MASK, !eq);
-        if (ne) return total + (__ffs(ne) - 1);
-        total += 32;
+        const int k0 = total + lane, k1 = k0 + 32;
+        uint32_t a0 = 0, b0 = 1, a1 = 0, b1 = 1;
+        if (k0 < limit) { a0 = a[k0]; b0 = b[k0]; }
+        if (k1 < limit) { a1 = a[k1]; b1 = b[k1]; }
+        const uint32_t n0 = __ballot_sync(FULL_MASK, a0 != b0);
+        if (n0) return total + (__ffs(n0) - 1);
+        const uint32_t n1 = __ballot_sync(FULL_MASK, a1 != b1);
+        if (n1) return total + 32 + (__ffs(n1) - 1);
+        total += 64;
     }
 }
 
