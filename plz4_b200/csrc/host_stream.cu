@@ -640,18 +640,20 @@ struct plz4cu_reader {
     }
     void quiesce() { engine_q.drain(); hash_q.drain(); }
 
-    // io.ReadFull: 0 = ok, 1 = clean EOF before any byte, -1 = short / error
+    // io.ReadFull: 0 = ok, 1 = clean EOF before any byte, -1 = short read or I/O error (an error is never an EOF)
     int read_full(uint8_t* p, size_t n, size_t* got)
     {
         size_t g = 0;
+        bool failed = false;
         while (g < n) {
             int64_t r = rd(ctx, p + g, n - g);
+            if (r < 0) failed = true;
             if (r <= 0) break;
             g += (size_t)r;
         }
         *got = g;
         if (g == n) return 0;
-        return g == 0 ? 1 : -1;
+        return (g == 0 && !failed) ? 1 : -1;
     }
 
     // header/read.go:26-119 + rdr/rdr.go:242-296.  Returns 0 ok, 1 clean EOF, <0 error.

@@ -157,3 +157,85 @@ def test_concurrent_streams(gpu, big):
     assert not errs, errs
     from plz4_b200 import _lib
     assert _lib.lib().plz4cu_host_outstanding() >= 0
+
+
+class FailAfter(io.RawIOBase):
+    """failReader (rd_test.go:1493-1505): hands out the bytes, then raises at the n-th read call."""
+    def __init__(self, data, ok_calls):
+        self.b, self.ok, self.n = io.BytesIO(data), ok_calls, 0
+    def readable(self): return True
+    def read(self, n=-1):
+        self.n += 1
+        if self.n > self.ok:
+            raise IOError("cable pulled")
+        return self.b.read(n)
+
+
+def test_failing_source_is_an_io_error_not_corruption(gpu, big):
+    """rd_test.go:959-1075, wr_test.go:852-1031: injected read failures at the n-th call, both flavours."""
+    f = compress(gpu, big[:20 * MiB], block_size_idx=4, block_checksum=True, pending_size=12 * MiB)
+    for parallel in (0, -1):
+        for ok in (0, 1, 3, 40, 200):
+            r = gpu.NewReader(FailAfter(f, ok), parallel=parallel, pending_size=12 * MiB)
+            out = bytearray()
+            with pytest.raises(gpu.StreamError) as e:
+                while True:
+                    chunk = r.read(MiB)
+                    if not chunk:
+                        break
+                    out += chunk
+            assert not gpu.lz4_corrupted(e.value), (parallel, ok, e.value.name)
+            assert bytes(out) == big[:len(out)] and len(out) % 65536 == 0       # whole blocks before the failure
+            with pytest.raises(gpu.StreamError):                                   # the error is sticky
+                r.read(1)
+            r.close()
+    # Writer.ReadFrom with a failing source: the error surfaces, Close afterwards is clean (already reported)
+    w = gpu.NewWriter(io.BytesIO(), block_size_idx=4, pending_size=12 * MiB)
+    with pytest.raises(gpu.StreamError) as e:
+        w.read_from(FailAfter(big, 5))
+    assert e.value.name == "ErrBlockRead"
+    w.close()
+
+
+def test_bad_seeker_and_early_close(gpu, big):
+    from plz4_b200 import _lib
+    L = _lib.lib()
+    marks = []
+    f = compress(gpu, big, block_size_idx=4, block_checksum=True, pending_size=12 * MiB, progress=lambda s, d: marks.append((s, d)))
+
+    class BadSeeker(io.BytesIO):                                                  # rd_test.go:1629-1640
+        def seek(self, *a):
+            raise IOError("no seeking today")
+    with pytest.raises(gpu.StreamError) as e:
+        decompress(gpu, BadSeeker(f).getvalue() and f, read_offset=3)             # misaligned offset
+    assert e.value.name == "ErrReadOffset"
+    r = gpu.NewReader(BadSeeker(f), read_offset=marks[5][1])
+    with pytest.raises(gpu.StreamError) as e:
+        r.read(10)
+    assert e.value.name == "ErrReadOffset"
+    r.close()
+
+    # slow consumer gives up early (rd_test.go:1180-1250): Close with a batch still being decoded ahead must neither
+    # hang nor touch the source afterwards, and every pinned slab goes back
+    import gc
+    del r, e
+    gc.collect()
+    before = L.plz4cu_host_outstanding()
+
+    def give_up_early():
+        src = io.BytesIO(f)
+        r = gpu.NewReader(src, pending_size=12 * MiB)
+        assert r.read(3 * MiB) == big[:3 * MiB]
+        r.close()
+        pos = src.tell()
+        with pytest.raises(gpu.StreamError) as e:
+            r.read(1)
+        assert e.value.name == "ErrClosed"
+        assert src.tell() == pos
+        # a writer dropped without Close finishes its queued work and frees its staging
+        w = gpu.NewWriter(io.BytesIO(), block_size_idx=4, pending_size=12 * MiB)
+        w.write(big[:30 * MiB])
+
+    give_up_early()
+    gc.collect()
+    assert L.plz4cu_host_outstanding() == before
