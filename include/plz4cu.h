@@ -136,6 +136,48 @@ PLZ4CU_API int plz4cu_pack_records_device(plz4cu_stream_t stream,
                                const void* rec_base, uint32_t rec_stride, const uint32_t* rec_len,
                                uint32_t nblk, void* packed, uint64_t* packed_off);
 
+/* ---------------------------------------------------------------- device-resident frames
+ * The frame walk of blk/frame.go:54-112 for a frame BODY that already sits in device memory:
+ * the offsets of all block records are found on the device, in parallel, so that a whole frame can be decoded
+ * without its bytes ever visiting the host.  `body` points at the first block's size word, `len` is the number of
+ * bytes available from there (it may run past the frame's end).  rec_off (device, `cap` entries) receives the
+ * body-relative offset of every record, ready for plz4cu_decompress_batch_device(rec_base = body).
+ * On return *nblk is the number of data blocks and *end_off the body offset just past the EndMark word.
+ * Returns 0, PLZ4CU_Z_BLOCK_SIZE_OVERFLOW, PLZ4CU_Z_BLOCK_READ (a record runs past `len`), PLZ4CU_Z_BLOCK_SIZE_READ
+ * (`len` ends where a size word should be), PLZ4CU_ERR_ARG (more than `cap` blocks) or PLZ4CU_ERR_CUDA.
+ * Synchronises `stream`. */
+PLZ4CU_API int plz4cu_frame_index_device(plz4cu_stream_t stream, const void* body, uint64_t len, uint32_t block_size,
+                              int block_checksum, uint64_t* rec_off, uint32_t cap, uint64_t* nblk, uint64_t* end_off);
+
+typedef struct plz4cu_frame_info {
+    uint32_t block_size;         /* bytes (descriptor/index.go:26-38)                                   */
+    uint32_t header_len;         /* bytes before the first block                                        */
+    int32_t  block_checksum, content_checksum, has_content_size, has_dict_id;
+    uint32_t dict_id;
+    uint32_t content_hash;       /* trailer value when content_checksum != 0 (NOT verified: serial xxh32) */
+    uint64_t content_size;
+    uint64_t nblk;               /* data blocks                                                         */
+    uint64_t frame_len;          /* bytes the frame occupies: header .. EndMark (+ content checksum)    */
+    uint64_t out_bytes;          /* decoded bytes in total                                              */
+    int32_t  contiguous;         /* 1: every block but the last is full, so dst holds the plain stream  */
+    int32_t  reserved0;
+} plz4cu_frame_info_t;
+
+/* Decode one whole LZ4 frame from device memory to device memory: header (header/read.go:26-119, fetched with one
+ * small copy), device-side frame walk, batched block decode with block-checksum verification.
+ *   frame, frame_len        : device pointer to the magic number; bytes available (may extend past the frame)
+ *   dst, dst_cap            : device output, slot b = dst + b*block_size; needs nblk*block_size <= dst_cap
+ *   rec_off, out_len, cap   : device scratch the caller owns (cap entries each); out_len[b] as for
+ *                             plz4cu_decompress_batch_device
+ * Returns 0 or the first error in stream order as a PLZ4CU_Z_* code (header, block hash / decode of the blocks
+ * before a broken walk, then the walk's own error; info->out_bytes counts what was decoded before it),
+ * PLZ4CU_Z_UNSUPPORTED for linked blocks, PLZ4CU_ERR_ARG when cap / dst_cap are too small: info (block size, block
+ * count, frame length) is filled in all the same, so a first call with cap == 0 sizes the buffers for the second.  The content checksum and content size are reported, not
+ * checked.  Synchronous. */
+PLZ4CU_API int plz4cu_decompress_frame_device(plz4cu_stream_t stream, const void* frame, uint64_t frame_len,
+                                   const plz4cu_dict_t* dict, void* dst, uint64_t dst_cap,
+                                   uint64_t* rec_off, int32_t* out_len, uint32_t cap, plz4cu_frame_info_t* info);
+
 /* Synthetic benchmark input (SURVEY.md §8d logtext): fills n bytes of stream `seed` starting at
  * 64 KiB segment `first_seg`.  Device pointer / host pointer flavours produce identical bytes. */
 PLZ4CU_API int plz4cu_gen_logtext_device(plz4cu_stream_t stream, uint32_t seed, uint64_t first_seg, void* dst, uint64_t n);

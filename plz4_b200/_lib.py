@@ -42,6 +42,8 @@ SIGNATURES = {
     "plz4cu_compress_batch_device": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _int, _int, _vp, _vp, _u32, _vp]),
     "plz4cu_decompress_batch_device": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _int, _int, _vp, _vp, _u64, _vp]),
     "plz4cu_pack_records_device": (_int, [_vp, _vp, _u32, _vp, _u32, _vp, _vp]),
+    "plz4cu_frame_index_device": (_int, [_vp, _vp, _u64, _u32, _int, _vp, _u32, _vp, _vp]),
+    "plz4cu_decompress_frame_device": (_int, [_vp, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
     "plz4cu_gen_logtext_device": (_int, [_vp, _u32, _u64, _vp, _u64]),
     "plz4cu_gen_logtext_host": (_int, [_u32, _u64, _vp, _u64]),
     "plz4cu_compress_batch_host": (_int, [_vp, _vp, _vp, _u32, _u32, _int, _int, _vp, _vp, _u64, _vp]),
@@ -96,6 +98,17 @@ class Opts(C.Structure):
         ("progress", PROGRESS_FN), ("progress_ctx", _vp),
         ("skip_cb", SKIP_FN), ("skip_ctx", _vp),
         ("dict_cb", DICT_FN), ("dict_ctx", _vp),
+    ]
+
+
+class FrameInfo(C.Structure):
+    """plz4cu_frame_info_t (include/plz4cu.h)."""
+    _fields_ = [
+        ("block_size", C.c_uint32), ("header_len", C.c_uint32),
+        ("block_checksum", C.c_int32), ("content_checksum", C.c_int32), ("has_content_size", C.c_int32), ("has_dict_id", C.c_int32),
+        ("dict_id", C.c_uint32), ("content_hash", C.c_uint32),
+        ("content_size", C.c_uint64), ("nblk", C.c_uint64), ("frame_len", C.c_uint64), ("out_bytes", C.c_uint64),
+        ("contiguous", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -140,6 +140,47 @@ def decompress_batch(recs, rec_off: Sequence[int], dst_cap: int, *, verify_check
     return out[:nblk], res[:nblk]
 
 
+# ---------------------------------------------------------------- device-resident frames
+
+def decompress_frame_device(frame, *, dict: Dict | None = None, stream=None):
+    """Decode one LZ4 frame held in a CUDA uint8 tensor without moving it to the host: header, device-side block
+    walk (blk/frame.go:54-112 done in parallel), batched decode with block-checksum verification.
+    Returns (out, info): `out` is a CUDA uint8 tensor of info.out_bytes decoded bytes, `info` the FrameInfo
+    (block size, block count, bytes the frame occupied, content checksum value: reported, not verified).
+    Raises stream.StreamError with the reference's error taxonomy on a malformed frame."""
+    import torch
+    from .stream import StreamError
+    L = _lib.lib()
+    assert frame.is_cuda and frame.dtype == torch.uint8 and frame.is_contiguous()
+    info = _lib.FrameInfo()
+    st = None if stream is None else C.c_void_p(stream)
+    fp = C.c_void_p(frame.data_ptr())
+    rc = L.plz4cu_decompress_frame_device(st, fp, frame.numel(), None, None, 0, None, None, 0, C.byref(info))   # sizing call
+    if rc < 0 and rc != _lib.ERR_ARG:
+        if rc > -100:
+            check(rc, "decompress_frame_device")
+        raise StreamError(rc)
+    nblk, bsz = int(info.nblk), int(info.block_size)
+    if nblk == 0:
+        return torch.empty(0, dtype=torch.uint8, device=frame.device), info
+    dst = torch.empty(nblk * bsz + 16, dtype=torch.uint8, device=frame.device)
+    rec_off = torch.empty(nblk, dtype=torch.int64, device=frame.device)
+    out_len = torch.empty(nblk, dtype=torch.int32, device=frame.device)
+    rc = L.plz4cu_decompress_frame_device(st, fp, frame.numel(), dict.handle if dict else None, C.c_void_p(dst.data_ptr()),
+                                          nblk * bsz, C.c_void_p(rec_off.data_ptr()), C.c_void_p(out_len.data_ptr()), nblk,
+                                          C.byref(info))
+    if rc < 0:
+        if rc > -100:
+            check(rc, "decompress_frame_device")
+        raise StreamError(rc)
+    if info.contiguous:
+        return dst[: int(info.out_bytes)], info
+    # blocks shorter than the block size in mid-stream (Flush): gather the pieces
+    lens = out_len.to(torch.int64)
+    parts = [dst[b * bsz: b * bsz + int(n)] for b, n in enumerate(lens.tolist())]
+    return torch.cat(parts), info
+
+
 # ---------------------------------------------------------------- raw block API (plz4_block.go)
 
 def compress_block(src, *, dst_cap: int | None = None, dict: Dict | None = None) -> bytes:

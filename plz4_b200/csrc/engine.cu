@@ -413,6 +413,119 @@ int plz4cu_gen_logtext_host(uint32_t seed, uint64_t first_seg, void* dst, uint64
     return 0;
 }
 
+// ---------------------------------------------------------------- device-resident frames
+
+int plz4cu_frame_index_device(plz4cu_stream_t stream, const void* body, uint64_t len, uint32_t block_size, int block_checksum,
+                              uint64_t* rec_off, uint32_t cap, uint64_t* nblk, uint64_t* end_off)
+{
+    if (int r = ensure_configured()) return r;
+    if (!body || !rec_off || !nblk || !end_off || block_size == 0) return fail(PLZ4CU_ERR_ARG, "frame_index_device: null pointer");
+    FrameIndexResult res{};
+    uint64_t launches = 0;
+    cudaError_t e = launch_frame_index(static_cast<const uint8_t*>(body), len, block_size, block_checksum, rec_off, cap, &res,
+                                       &launches, static_cast<cudaStream_t>(stream));
+    g_launches += launches;
+    if (e != cudaSuccess) return fail(PLZ4CU_ERR_CUDA, "frame_index_device", e);
+    *nblk = res.nblk;
+    *end_off = res.stop_off + (res.why == 1 ? 4 : 0);
+    switch (res.why) {
+    case 1: break;
+    case 2: return PLZ4CU_Z_BLOCK_SIZE_OVERFLOW;
+    case 3: return PLZ4CU_Z_BLOCK_READ;
+    default: return PLZ4CU_Z_BLOCK_SIZE_READ;
+    }
+    if (res.nblk > cap) return fail(PLZ4CU_ERR_ARG, "frame_index_device: more blocks than rec_off can hold");
+    return 0;
+}
+
+int plz4cu_decompress_frame_device(plz4cu_stream_t stream, const void* frame, uint64_t frame_len, const plz4cu_dict_t* dict,
+                                   void* dst, uint64_t dst_cap, uint64_t* rec_off, int32_t* out_len, uint32_t cap,
+                                   plz4cu_frame_info_t* info)
+{
+    if (int r = ensure_configured()) return r;
+    if (!frame || !info) return fail(PLZ4CU_ERR_ARG, "decompress_frame_device: null pointer");
+    memset(info, 0, sizeof *info);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint8_t* f = static_cast<const uint8_t*>(frame);
+
+    // header/read.go:26-119 on the first <= 19 bytes
+    uint8_t h[19] = {0};
+    const size_t hn = (size_t)std::min<uint64_t>(frame_len, sizeof h);
+    CU(cudaMemcpyAsync(h, f, hn, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (hn < 7) return PLZ4CU_Z_HEADER_READ;
+    static const uint8_t magic[4] = {0x04, 0x22, 0x4d, 0x18};
+    if (memcmp(h, magic, 4) != 0) return PLZ4CU_Z_MAGIC;
+    const uint8_t flags = h[4], bd = h[5];
+    if (((flags >> 6) & 3) != 1) return PLZ4CU_Z_VERSION;
+    if (flags & 0x02) return PLZ4CU_Z_RESERVE_BIT;
+    if (((bd >> 4) & 7) < 4 || (bd & 0x80) || (bd & 0x0F)) return PLZ4CU_Z_BLOCK_DESCRIPTOR;
+    size_t n = 7;
+    if (flags & 0x08) n += 8;
+    if (flags & 0x01) n += 4;
+    if (hn < n) return PLZ4CU_Z_HEADER_READ;
+    if (flags & 0x08) for (int i = 0; i < 8; i++) info->content_size |= (uint64_t)h[6 + i] << (8 * i);
+    if (flags & 0x01) memcpy(&info->dict_id, h + n - 5, 4);
+    if (((plz4cu_xxh32_host(h + 4, n - 5) >> 8) & 0xFF) != h[n - 1]) return PLZ4CU_Z_HEADER_HASH;
+    info->block_size = 1u << (8 + 2 * ((bd >> 4) & 7));                 // 4..7 -> 64 KiB .. 4 MiB
+    info->header_len = (uint32_t)n;
+    info->block_checksum = (flags >> 4) & 1;
+    info->content_checksum = (flags >> 2) & 1;
+    info->has_content_size = (flags >> 3) & 1;
+    info->has_dict_id = flags & 1;
+    if (!(flags & 0x20)) return PLZ4CU_Z_UNSUPPORTED;                   // linked blocks decode in order on CPU cores
+
+    uint64_t nblk = 0, end_off = 0;
+    int rc;
+    if (!rec_off || !out_len || cap == 0) {
+        // sizing call: count the blocks only
+        uint64_t* one = nullptr;
+        CU(cudaMalloc((void**)&one, sizeof(uint64_t)));
+        rc = plz4cu_frame_index_device(stream, f + n, frame_len - n, info->block_size, info->block_checksum, one, 0, &nblk, &end_off);
+        cudaFree(one);
+        cap = 0;
+    } else {
+        rc = plz4cu_frame_index_device(stream, f + n, frame_len - n, info->block_size, info->block_checksum, rec_off, cap,
+                                       &nblk, &end_off);
+    }
+    info->nblk = nblk;
+    if (rc == PLZ4CU_ERR_CUDA) return rc;
+    // a broken walk is reported AFTER the blocks before the break were decoded and checked: the first error in
+    // stream order wins, as with the host reader (a wrong size word usually shows up as that block's hash mismatch)
+    const int walk_rc = (rc == PLZ4CU_ERR_ARG) ? 0 : rc;
+    if (walk_rc == 0) {
+        info->frame_len = n + end_off + (info->content_checksum ? 4 : 0);
+        if (info->frame_len > frame_len) return PLZ4CU_Z_CONTENT_HASH_READ;
+        if (info->content_checksum) {
+            uint8_t c[4];
+            CU(cudaMemcpyAsync(c, f + n + end_off, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            memcpy(&info->content_hash, c, 4);
+        }
+    }
+    if (nblk == 0) { info->contiguous = 1; return walk_rc; }
+    if (nblk > cap) return fail(PLZ4CU_ERR_ARG, "decompress_frame_device: scratch holds fewer entries than the frame has blocks");
+    if (!dst || nblk * (uint64_t)info->block_size > dst_cap) return fail(PLZ4CU_ERR_ARG, "decompress_frame_device: dst too small");
+    rc = plz4cu_decompress_batch_device(stream, f + n, rec_off, nullptr, (uint32_t)nblk, info->block_size, info->block_checksum, 0,
+                                        dict, dst, info->block_size, out_len);
+    if (rc < 0) return rc;
+    std::vector<int32_t> lens(nblk);
+    CU(cudaMemcpyAsync(lens.data(), out_len, nblk * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    info->contiguous = 1;
+    for (uint64_t b = 0; b < nblk; b++) {
+        const int32_t r = lens[b];
+        if (r < 0) {
+            if (r == PLZ4CU_E_BLOCKHASH) return PLZ4CU_Z_BLOCK_HASH;
+            if (r == PLZ4CU_E_OVERFLOW) return PLZ4CU_Z_BLOCK_SIZE_OVERFLOW;
+            return PLZ4CU_Z_DECOMPRESS;
+        }
+        info->out_bytes += (uint64_t)r;
+        if (b + 1 < nblk && (uint32_t)r != info->block_size) info->contiguous = 0;
+    }
+    return walk_rc;
+}
+
 // ---------------------------------------------------------------- host-resident batches
 //
 // Blocks are cut into chunks and software-pipelined over kLanes lanes (stream + private scratch

@@ -51,6 +51,17 @@ int compress_hash_bits(uint32_t dst_cap);          // table size the encoder wil
 
 cudaError_t launch_pack(const uint8_t* rec_base, uint32_t rec_stride, const uint32_t* rec_len, uint32_t nblk,
                         uint8_t* packed, uint64_t* packed_off, cudaStream_t stream);
+cudaError_t launch_scan_u32(const uint32_t* len, uint32_t n, uint64_t* off, cudaStream_t stream);   // exclusive, off[n] = total
+
+// Block boundaries of a device-resident frame body (frame_index.cu).  Synchronises `stream`.
+struct FrameIndexResult {
+    uint64_t nblk;         // data blocks found before the walk stopped
+    uint32_t why;          // 1 EndMark reached, 2 size word above the block size, 3 record runs past the body,
+                           // 4 body ends where a size word should be
+    uint64_t stop_off;     // body offset where it stopped (the EndMark when why == 1)
+};
+cudaError_t launch_frame_index(const uint8_t* body, uint64_t len, uint32_t bsz, int blk_check, uint64_t* rec_off, uint32_t cap,
+                               FrameIndexResult* out, uint64_t* launches, cudaStream_t stream);
 cudaError_t launch_xxh32(const uint8_t* base, const uint64_t* off, const uint32_t* len, uint32_t nblk,
                          uint32_t* out, cudaStream_t stream);
 cudaError_t launch_gen_logtext(uint32_t seed, uint64_t first_seg, uint8_t* dst, uint64_t n, cudaStream_t stream);

@@ -58,6 +58,12 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const uint8_t* __rest
     warp_copy(packed + off[b], rec_base + (uint64_t)b * rec_stride, rec_len[b], lane);
 }
 
+cudaError_t launch_scan_u32(const uint32_t* len, uint32_t n, uint64_t* off, cudaStream_t stream)
+{
+    scan_lengths_kernel<<<1, 1024, 0, stream>>>(len, n, off);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack(const uint8_t* rec_base, uint32_t rec_stride, const uint32_t* rec_len, uint32_t nblk,
                         uint8_t* packed, uint64_t* packed_off, cudaStream_t stream)
 {
