@@ -178,6 +178,16 @@ PLZ4CU_API int plz4cu_decompress_frame_device(plz4cu_stream_t stream, const void
                                    const plz4cu_dict_t* dict, void* dst, uint64_t dst_cap,
                                    uint64_t* rec_off, int32_t* out_len, uint32_t cap, plz4cu_frame_info_t* info);
 
+/* The writer's side of the same: n device-resident bytes become ONE complete LZ4 frame in device memory (header,
+ * block records in order as async/writer.go:316-348 would write them, EndMark) — byte for byte what NewWriter produces
+ * from the same bytes and options.  Honoured options: block size, block checksum, content size, dictionary id; level
+ * must be 1 and blocks independent.  A content checksum is refused with PLZ4CU_Z_UNSUPPORTED: it is a serial xxh32 of
+ * the whole input and stays a host-side job.  frame_cap: header + ceil(n/bsz)*(bsz+8) + 4 always suffices; returns
+ * PLZ4CU_ERR_ARG when the frame does not fit.  Synchronous. */
+struct plz4cu_opts;                                   /* plz4cu_opts_t, defined with the frame streams below */
+PLZ4CU_API int plz4cu_compress_frame_device(plz4cu_stream_t stream, const void* src, uint64_t n, const struct plz4cu_opts* opts,
+                                 const plz4cu_dict_t* dict, void* frame, uint64_t frame_cap, uint64_t* frame_len);
+
 /* Synthetic benchmark input (SURVEY.md §8d logtext): fills n bytes of stream `seed` starting at
  * 64 KiB segment `first_seg`.  Device pointer / host pointer flavours produce identical bytes. */
 PLZ4CU_API int plz4cu_gen_logtext_device(plz4cu_stream_t stream, uint32_t seed, uint64_t first_seg, void* dst, uint64_t n);
@@ -348,6 +358,9 @@ PLZ4CU_API size_t plz4cu_membuf_len(const plz4cu_membuf_t* m);
 PLZ4CU_API int64_t plz4cu_membuf_read(void* ctx, void* buf, size_t n);
 PLZ4CU_API int64_t plz4cu_membuf_write(void* ctx, const void* data, size_t n);
 PLZ4CU_API int plz4cu_membuf_seek(void* ctx, int64_t delta);
+
+/* header/write.go:23-73: the frame header these options produce (7..19 bytes incl. the HC byte); returns its length. */
+PLZ4CU_API int plz4cu_frame_header(const plz4cu_opts_t* opts, uint8_t out[19]);
 
 /* xxh32.ChecksumZero of a host buffer, computed on the host (header HC byte, content checksum). */
 PLZ4CU_API uint32_t plz4cu_xxh32_host(const void* p, size_t n);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "plz4cu_pack_records_device": (_int, [_vp, _vp, _u32, _vp, _u32, _vp, _vp]),
     "plz4cu_frame_index_device": (_int, [_vp, _vp, _u64, _u32, _int, _vp, _u32, _vp, _vp]),
     "plz4cu_decompress_frame_device": (_int, [_vp, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u32, _vp]),
+    "plz4cu_compress_frame_device": (_int, [_vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
     "plz4cu_gen_logtext_device": (_int, [_vp, _u32, _u64, _vp, _u64]),
     "plz4cu_gen_logtext_host": (_int, [_u32, _u64, _vp, _u64]),
     "plz4cu_compress_batch_host": (_int, [_vp, _vp, _vp, _u32, _u32, _int, _int, _vp, _vp, _u64, _vp]),
@@ -70,6 +71,7 @@ SIGNATURES = {
     "plz4cu_reader_free": (None, [_vp]),
     "plz4cu_write_skip_frame_header": (_int, [_vp, _vp, C.c_uint8, _u32]),
     "plz4cu_xxh32_host": (_u32, [_vp, _sz]),
+    "plz4cu_frame_header": (_int, [_vp, _vp]),
     "plz4cu_membuf_new": (_vp, [_vp, _sz, _sz]),
     "plz4cu_membuf_free": (None, [_vp]),
     "plz4cu_membuf_len": (_sz, [_vp]),

@@ -181,6 +181,29 @@ def decompress_frame_device(frame, *, dict: Dict | None = None, stream=None):
     return torch.cat(parts), info
 
 
+def compress_frame_device(src, *, dict: Dict | None = None, stream=None, **options):
+    """n bytes of a CUDA uint8 tensor -> one complete LZ4 frame in a CUDA uint8 tensor, byte for byte what NewWriter
+    writes for the same bytes and options (block_size_idx, block_checksum, content_size, dict_id; no content checksum)."""
+    import torch
+    from .stream import StreamError, _opts
+    L = _lib.lib()
+    assert src.is_cuda and src.dtype == torch.uint8 and src.is_contiguous()
+    options.setdefault("content_checksum", False)
+    o, keep = _opts(**options)
+    bsz = 1 << (8 + 2 * int(o.block_size_idx))
+    n = src.numel()
+    cap = 19 + ((n + bsz - 1) // bsz) * (bsz + 8) + 4
+    frame = torch.empty(cap, dtype=torch.uint8, device=src.device)
+    flen = C.c_uint64()
+    rc = L.plz4cu_compress_frame_device(None if stream is None else C.c_void_p(stream), C.c_void_p(src.data_ptr()), n, C.byref(o),
+                                        dict.handle if dict else None, C.c_void_p(frame.data_ptr()), cap, C.byref(flen))
+    if rc < 0:
+        if rc > -100:
+            check(rc, "compress_frame_device")
+        raise StreamError(rc)
+    return frame[: flen.value]
+
+
 # ---------------------------------------------------------------- raw block API (plz4_block.go)
 
 def compress_block(src, *, dst_cap: int | None = None, dict: Dict | None = None) -> bytes:

@@ -526,6 +526,62 @@ int plz4cu_decompress_frame_device(plz4cu_stream_t stream, const void* frame, ui
     return walk_rc;
 }
 
+int plz4cu_compress_frame_device(plz4cu_stream_t stream, const void* src, uint64_t n, const plz4cu_opts_t* opts,
+                                 const plz4cu_dict_t* dict, void* frame, uint64_t frame_cap, uint64_t* frame_len)
+{
+    if (int r = ensure_configured()) return r;
+    if (!frame || !frame_len || (!src && n)) return fail(PLZ4CU_ERR_ARG, "compress_frame_device: null pointer");
+    plz4cu_opts_t o;
+    if (opts) o = *opts; else plz4cu_opts_default(&o);
+    if (o.level > 1 || o.block_linked || o.content_checksum) return PLZ4CU_Z_UNSUPPORTED;
+    uint8_t hdr[19];
+    const uint64_t hn = (uint64_t)plz4cu_frame_header(&o, hdr);
+    const uint32_t bsz = 1u << (8 + 2 * ((hdr[5] >> 4) & 7));
+    if (n / bsz >= 0xFFFFFFF0ull) return fail(PLZ4CU_ERR_ARG, "compress_frame_device: too many blocks for one call");
+    const uint32_t nblk = (uint32_t)((n + bsz - 1) / bsz);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* out = static_cast<uint8_t*>(frame);
+    if (frame_cap < hn + 4) return fail(PLZ4CU_ERR_ARG, "compress_frame_device: frame buffer too small");
+    CU(cudaMemcpyAsync(out, hdr, hn, cudaMemcpyHostToDevice, st));
+    uint64_t total = 0;
+    if (nblk) {
+        // scratch: block table, record slots, record lengths, packed offsets
+        const uint32_t stride = round_up16(bsz + PLZ4CU_REC_OVERHEAD);
+        const uint64_t tbl_bytes = ((uint64_t)nblk * 12 + 15) & ~15ull, len_bytes = ((uint64_t)nblk * 4 + 15) & ~15ull;
+        const uint64_t bytes = tbl_bytes + (uint64_t)nblk * stride + len_bytes + (uint64_t)(nblk + 1) * 8;
+        uint8_t* scratch = nullptr;
+        CU(cudaMallocAsync((void**)&scratch, bytes, st));
+        uint64_t* d_off = reinterpret_cast<uint64_t*>(scratch);
+        uint32_t* d_len = reinterpret_cast<uint32_t*>(d_off + nblk);
+        uint8_t* d_rec = scratch + tbl_bytes;
+        uint32_t* d_rl = reinterpret_cast<uint32_t*>(d_rec + (uint64_t)nblk * stride);
+        uint64_t* d_poff = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(d_rl) + len_bytes);
+        std::vector<uint64_t> tbl((tbl_bytes + 7) / 8);
+        uint32_t* h_len = reinterpret_cast<uint32_t*>(tbl.data() + nblk);
+        for (uint32_t b = 0; b < nblk; b++) { tbl[b] = (uint64_t)b * bsz; h_len[b] = (uint32_t)std::min<uint64_t>(bsz, n - tbl[b]); }
+        int rc = 0;
+        cudaError_t e = cudaMemcpyAsync(scratch, tbl.data(), (uint64_t)nblk * 12, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            rc = plz4cu_compress_batch_device(stream, src, d_off, d_len, nblk, bsz, o.block_checksum, 0, dict, d_rec, stride, d_rl);
+            if (rc == 0) e = launch_scan_u32(d_rl, nblk, d_poff, st);
+        }
+        if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(&total, d_poff + nblk, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess && rc == 0) {
+            if (hn + total + 4 > frame_cap) rc = fail(PLZ4CU_ERR_ARG, "compress_frame_device: frame buffer too small");
+            else e = launch_pack(d_rec, stride, d_rl, nblk, out + hn, d_poff, st);
+        }
+        g_launches += 3;
+        cudaFreeAsync(scratch, st);
+        if (e != cudaSuccess) return fail(PLZ4CU_ERR_CUDA, "compress_frame_device", e);
+        if (rc < 0) return rc;
+    }
+    CU(cudaMemsetAsync(out + hn + total, 0, 4, st));                  // EndMark (trailer/trailer.go:10-19)
+    CU(cudaStreamSynchronize(st));
+    *frame_len = hn + total + 4;
+    return 0;
+}
+
 // ---------------------------------------------------------------- host-resident batches
 //
 // Blocks are cut into chunks and software-pipelined over kLanes lanes (stream + private scratch

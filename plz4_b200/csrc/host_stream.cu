@@ -1060,6 +1060,14 @@ int plz4cu_write_skip_frame_header(plz4cu_write_fn wr, void* wr_ctx, uint8_t nib
 
 uint32_t plz4cu_xxh32_host(const void* p, size_t n) { return xxh32_once(p, n); }
 
+int plz4cu_frame_header(const plz4cu_opts_t* opts, uint8_t out[19])
+{
+    Opts o(opts);                                    // same normalisation as NewWriter (block size default, level clamp)
+    const std::vector<uint8_t> h = make_header(o.o);
+    memcpy(out, h.data(), h.size());
+    return (int)h.size();
+}
+
 // ---- in-memory endpoints (bytes.Reader / bytes.Buffer for C callers)
 struct plz4cu_membuf { uint8_t* data; size_t len, cap, pos; };
 plz4cu_membuf_t* plz4cu_membuf_new(void* data, size_t len, size_t cap)

@@ -119,3 +119,27 @@ def test_flushed_short_blocks_and_big_blocks(gpu, port):
     frame = F.write_frame(big, F.Opts(block_idx=7, block_checksum=True, content_checksum=True), port)   # reference-side writer
     out, info = gpu.decompress_frame_device(dev(frame))
     assert bytes(out.cpu().numpy()) == big and info.nblk == 6 and info.frame_len == len(frame)
+
+
+def test_compress_frame_device_equals_the_host_writer(gpu, port, mixed):
+    """The device-side writer emits byte for byte the frame NewWriter produces (same blocks, same order, same header)."""
+    data = mixed[90 * MiB: 130 * MiB + 777]
+    d = dev(data)
+    for opts in (dict(block_size_idx=4, block_checksum=True), dict(block_size_idx=5), dict(block_size_idx=7, block_checksum=True, content_size=len(data), dict_id=77)):
+        frame = gpu.compress_frame_device(d, **opts)
+        fb = bytes(frame.cpu().numpy())
+        assert fb == compress(gpu, data, content_checksum=False, **opts)
+        assert F.read_frames(fb, port) == data                            # the independent decoder accepts it
+        out, info = gpu.decompress_frame_device(frame)                    # and device -> device closes the loop
+        assert torch.equal(out, d) and info.frame_len == len(fb)
+    # empty input: header + EndMark (wr_test.go: zero-length streams)
+    e = gpu.compress_frame_device(torch.empty(0, dtype=torch.uint8, device="cuda"), block_size_idx=4)
+    assert bytes(e.cpu().numpy()) == compress(gpu, b"", block_size_idx=4, content_checksum=False)
+    with pytest.raises(gpu.StreamError) as ex:                            # serial content checksum: host-side job
+        gpu.compress_frame_device(d, content_checksum=True)
+    assert ex.value.name == "ErrUnsupported"
+    dct = gpu.Dict(mixed[:65536])
+    frame = gpu.compress_frame_device(d[: 3 * MiB], dict=dct, block_size_idx=4, block_checksum=True, dict_id=5)
+    out, info = gpu.decompress_frame_device(frame, dict=dct)
+    assert torch.equal(out, d[: 3 * MiB]) and info.dict_id == 5
+    assert F.read_frames(bytes(frame.cpu().numpy()), port, dictionary=mixed[:65536]) == data[: 3 * MiB]
