@@ -269,18 +269,57 @@ def run_gpu(args) -> None:
         h_src.copy_(src[:e_bytes])
         h_packed = torch.empty(e_blk * (BSZ + 8), dtype=torch.uint8).pin_memory()
         h_out = torch.empty(e_bytes, dtype=torch.uint8).pin_memory()
-        h_off = np.arange(e_blk, dtype=np.uint64) * BSZ
         h_len = np.full(e_blk, BSZ, dtype=np.uint32)
-        h_poff = np.zeros(e_blk + 1, dtype=np.uint64)
         h_res = np.zeros(e_blk, dtype=np.int32)
         vp = lambda a: C.c_void_p(a.ctypes.data)
-        hp = lambda t: C.c_void_p(t.data_ptr())
+        # The step is cut into parts: part k is decompressed (D2H-heavy) while part k+1 is still being compressed
+        # (H2D-heavy), two caller threads making the same two public calls — PCIe is full duplex and the engine
+        # gives every concurrent call its own pipeline.  --e2e-parts 1 runs the two passes strictly one after the other.
+        n_parts = max(1, min(args.e2e_parts, e_blk))
+        cuts = [e_blk * k // n_parts for k in range(n_parts + 1)]
+        parts = []
+        for k in range(n_parts):
+            b0, b1 = cuts[k], cuts[k + 1]
+            parts.append({"b0": b0, "nb": b1 - b0, "off": np.arange(b1 - b0, dtype=np.uint64) * BSZ,
+                          "poff": np.zeros(b1 - b0 + 1, dtype=np.uint64), "ready": threading.Event(),
+                          "src": C.c_void_p(h_src.data_ptr() + b0 * BSZ), "out": C.c_void_p(h_out.data_ptr() + b0 * BSZ),
+                          "packed": C.c_void_p(h_packed.data_ptr() + b0 * (BSZ + 8)), "cap": (b1 - b0) * (BSZ + 8)})
+        errors = []
+
+        def compress_parts():
+            try:
+                check(L.plz4cu_init(local), "plz4cu_init")          # a new thread starts on device 0
+                for q in parts:
+                    check(L.plz4cu_compress_batch_host(q["src"], vp(q["off"]), vp(h_len[q["b0"]:]), q["nb"], BSZ, 1, 0, None,
+                                                       q["packed"], q["cap"], vp(q["poff"])), "compress_batch_host")
+                    q["ready"].set()
+            except BaseException as ex:          # noqa: BLE001 - re-raised on the main thread
+                errors.append(ex)
+                for q in parts:
+                    q["ready"].set()
+
+        def decompress_parts():
+            try:
+                check(L.plz4cu_init(local), "plz4cu_init")
+                for q in parts:
+                    q["ready"].wait()
+                    if errors:
+                        return
+                    check(L.plz4cu_decompress_batch_host(q["packed"], int(q["poff"][q["nb"]]), vp(q["poff"]), None, q["nb"], BSZ, 1, 0,
+                                                         None, q["out"], BSZ, vp(h_res[q["b0"]:])), "decompress_batch_host")
+            except BaseException as ex:          # noqa: BLE001
+                errors.append(ex)
 
         def e2e_step():
-            check(L.plz4cu_compress_batch_host(hp(h_src), vp(h_off), vp(h_len), e_blk, BSZ, 1, 0, None,
-                                               hp(h_packed), h_packed.numel(), vp(h_poff)), "compress_batch_host")
-            check(L.plz4cu_decompress_batch_host(hp(h_packed), int(h_poff[e_blk]), vp(h_poff), None, e_blk, BSZ, 1, 0, None,
-                                                 hp(h_out), BSZ, vp(h_res)), "decompress_batch_host")
+            for q in parts:
+                q["ready"].clear()
+            ts = [threading.Thread(target=compress_parts), threading.Thread(target=decompress_parts)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            if errors:
+                raise errors[0]
         for _ in range(max(1, min(args.warmup, 3))):
             e2e_step()
         assert (h_res == BSZ).all() and torch.equal(h_out, h_src), "e2e round trip mismatch"
@@ -291,8 +330,8 @@ def run_gpu(args) -> None:
             e2e_step()
         barrier()
         te = time.perf_counter() - t0
-        c_e = int(h_poff[e_blk])
-        e2e = {"t": te, "steps": e_steps, "bytes": e_bytes,
+        c_e = sum(int(q["poff"][q["nb"]]) for q in parts)
+        e2e = {"t": te, "steps": e_steps, "bytes": e_bytes, "parts": n_parts,
                "h2d": e_bytes + c_e + e_blk * 24, "d2h": c_e + e_bytes + e_blk * 12 + 8}
         del h_src, h_packed, h_out
 
@@ -351,7 +390,7 @@ def run_gpu(args) -> None:
         line["e2e"] = {"value": round(world * 2 * e2e["bytes"] * e2e["steps"] / te_max / 1e9, 3), "unit": UNIT,
                        "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                        "bytes_per_gpu": int(e2e["bytes"]), "steps": e2e["steps"],
-                       "api": "plz4cu_compress_batch_host + plz4cu_decompress_batch_host, pinned host buffers"}
+                       "api": "plz4cu_compress_batch_host + plz4cu_decompress_batch_host, pinned host buffers, %d parts: part k decompresses while part k+1 compresses" % e2e["parts"]}
     if not args.no_cpu and world == 1:       # reported on rank 0 at N=1 only
         try:
             r = cpu_reference(args.cpu_sample_mib << 20, 3, 1)
@@ -371,6 +410,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="plz4_b200", choices=["plz4_b200", "reference"])
     ap.add_argument("--gib", type=float, default=8.0, help="uncompressed GiB per GPU (configs[1] = 8)")
+    ap.add_argument("--e2e-parts", type=int, default=8, help="parts the e2e step is cut into (decompress of part k overlaps compress of part k+1); 1 = strictly sequential passes")
     ap.add_argument("--e2e-gib", type=float, default=8.0, help="GiB per GPU pushed through the host-buffer API per step")
     ap.add_argument("--cpu-sample-mib", type=int, default=2048, help="bounded sample for the CPU baseline / reference arm")
     ap.add_argument("--no-e2e", action="store_true")
