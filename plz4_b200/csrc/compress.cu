@@ -168,8 +168,8 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
                 const uint32_t hv = table_slot(own4(q), kHashBits);
                 const uint32_t same = __match_any_sync(FULL_MASK, hv);
                 if ((same >> lane) == 1u) table[hv] = (uint16_t)q;
+                __syncwarp();                        // a later group may overwrite the same slot: keep the order
             }
-            __syncwarp();
         }
         const int lo_cand = kFrag ? 1 - min(prefix, 65535) : 1;      // lowest usable candidate position
         const uintptr_t da = reinterpret_cast<uintptr_t>(dict);

@@ -215,8 +215,10 @@ cudaError_t launch_frame_index(const uint8_t* body, uint64_t len, uint32_t bsz, 
         return e2;
     };
     // few blocks: the serial walk is short, and accidental candidates would swamp the real ones
-    static const bool force_walk = getenv("PLZ4CU_SERIAL_WALK") != nullptr;      // measurement knob
-    if (len / bsz <= 1024 || force_walk) {
+    // measurement / test knobs: force the one-thread walk, or let small frames take the parallel path
+    static const bool force_walk = getenv("PLZ4CU_SERIAL_WALK") != nullptr;
+    static const uint64_t min_blocks = getenv("PLZ4CU_WALK_MIN_BLOCKS") ? strtoull(getenv("PLZ4CU_WALK_MIN_BLOCKS"), nullptr, 10) : 1024;
+    if (len / bsz <= min_blocks || force_walk) {
         e = walk();
         cudaFreeAsync(d_result, stream);
         return e;
