@@ -142,7 +142,7 @@ struct Pipe {
 // Host-resident calls from different threads (many writers / readers, the reference's one-goroutine-per-stream use)
 // each lease a whole pipe, so their copies and kernels overlap on the device; up to kMaxPipes per device, further
 // callers queue for a free one.
-constexpr int kMaxPipes = 4;
+constexpr int kMaxPipes = 8;
 struct PipePool {
     std::mutex mu;
     std::condition_variable cv;

@@ -204,7 +204,7 @@ const uint8_t kMagic[4] = {0x04, 0x22, 0x4d, 0x18};
 constexpr uint32_t kSkipMagic = 0x184D2A50u;
 // Bytes of blocks gathered per engine call when batching (n_parallel != 0) and no pending size is given: enough blocks
 // to occupy the GPU (one warp or one 64 KiB fragment per block), small enough that staging, engine and sink overlap.
-constexpr size_t kAutoBatchMin = 64u << 20, kAutoBatchMax = 256u << 20;
+constexpr size_t kAutoBatchMin = 64u << 20, kAutoBatchMax = 128u << 20;
 constexpr size_t kAutoBatchBlocks = 256;
 constexpr size_t kSmallStage = 8u << 20;             // streams shorter than this never touch pinned memory
 
@@ -597,10 +597,12 @@ struct plz4cu_reader {
     uint64_t hdr_content_size = 0, content_acc = 0;
     XXH32 hasher;
 
-    // Decoded blocks arrive in batches.  When batching (n_parallel != 0) the engine thread reads and decodes batch
-    // k+1 while the caller drains batch k (async/reader.go:128-221's read-ahead), and the content checksum of the
-    // decoded bytes runs on its own thread (async/hash.go); batches grow from small to full size so that a short
-    // stream neither waits for nor pins a full-size staging area.
+    // Decoded blocks arrive in batches.  When batching (n_parallel != 0) a source thread reads the records of the next
+    // batches while earlier ones are being decoded and the caller drains the current one (async/reader.go:128-221's
+    // read-ahead); every batch slot decodes on its own engine thread, so several batches can be on the GPU at once —
+    // a batch of large blocks keeps only a few warps busy, and only concurrency between batches fills the device.
+    // The content checksum of the decoded bytes runs on its own thread (async/hash.go).  Batches grow from small to
+    // full size so that a short stream neither waits for nor pins a full-size staging area.
     struct Batch {
         PinnedBuf recs, out;
         size_t recs_len = 0;
@@ -613,18 +615,26 @@ struct plz4cu_reader {
         uint32_t content_hash_read = 0;
         uint32_t tail_read = 0;                       // bytes consumed by a failed trailing read (for src_pos)
         uint32_t digest = 0;                          // content checksum up to the end of this batch
-        uint64_t ticket = 0, hash_ticket = 0;
+        uint64_t ticket = 0, hash_ticket = 0;         // decode job on engine_q[slot], hash job on hash_q
     };
-    Batch bt[2];
-    int cb = 0;                                       // batch the caller is draining
-    bool prefetched = false;                          // bt[cb ^ 1] is being (or has been) filled ahead
+    static constexpr int kSlots = 8;
+    Batch bt[kSlots];
+    // ring bookkeeping: batch number k lives in slot k % kSlots.  `produced` batches have been read (decode submitted),
+    // `released` have been handed back by the caller; the source loop runs while produced - released <= depth.
+    std::mutex ring_mu;
+    std::condition_variable ring_cv;
+    uint64_t produced = 0, released = 0;
+    bool source_done = true, stop_source = false;
+    uint64_t cb_index = 0;                            // batch the caller is draining (valid while have_batch)
+    bool have_batch = false;
     size_t next_batch_bytes = 0;
     const bool async;
     const int device;
     uint32_t cur = 0, run_first = 0;                  // next block to serve; first block of the piece being served
     size_t cur_off = 0, cur_len = 0;
     bool have_block = false;
-    SerialExec engine_q, hash_q;
+    SerialExec source_q, engine_q[kSlots], hash_q;
+    Batch& cbatch() { return bt[cb_index % kSlots]; }
 
     plz4cu_reader(plz4cu_read_fn r, plz4cu_seek_fn s, void* c, const plz4cu_opts_t* o)
         : rd(r), seek(s), ctx(c), opt(o), async(opt.o.n_parallel != 0), device(current_device())
@@ -638,7 +648,15 @@ struct plz4cu_reader {
         quiesce();
         if (dict) plz4cu_dict_destroy(dict);
     }
-    void quiesce() { engine_q.drain(); hash_q.drain(); }
+    void quiesce()
+    {
+        { std::lock_guard<std::mutex> lk(ring_mu); stop_source = true; }
+        ring_cv.notify_all();
+        source_q.drain();
+        for (SerialExec& q : engine_q) q.drain();
+        hash_q.drain();
+        stop_source = false;
+    }
 
     // io.ReadFull: 0 = ok, 1 = clean EOF before any byte, -1 = short read or I/O error (an error is never an EOF)
     int read_full(uint8_t* p, size_t n, size_t* got)
@@ -746,21 +764,20 @@ struct plz4cu_reader {
             content_acc = 0;
             quiesce();                                  // no read-ahead or hashing crosses a frame boundary
             hasher.reset();
-            prefetched = false;
-            bt[0].nblk = bt[1].nblk = 0; bt[0].tail_event = bt[1].tail_event = 0;
+            have_batch = false;
+            for (Batch& b : bt) { b.nblk = 0; b.tail_event = 0; }
             cur = 0;
             in_body = true;
             return 0;
         }
     }
 
-    // blk/frame.go:54-112 for up to `want_bytes` of blocks, then one engine call.  Engine thread when async.
-    void fill_batch(Batch& b, size_t want_bytes)
+    // blk/frame.go:54-112 for up to `want_bytes` of blocks: the records of one batch, in order (source thread).
+    void read_records(Batch& b, size_t want_bytes)
     {
         const size_t batch_blocks = std::max<size_t>(1, want_bytes / (size_t)bsz);
-        if (b.hash_ticket) hash_q.wait(b.hash_ticket);  // the previous tenant of these buffers may still be hashed
         b.recs_len = 0; b.rec_off.clear(); b.rec_read.clear();
-        b.nblk = 0; b.tail_event = 0; b.tail_read = 0; b.hash_ticket = 0;
+        b.nblk = 0; b.tail_event = 0; b.tail_read = 0; b.hash_ticket = 0; b.ticket = 0;
         uint32_t nblk = 0;
         while (nblk < batch_blocks) {
             uint8_t w[4];
@@ -798,24 +815,30 @@ struct plz4cu_reader {
             b.rec_read.push_back((uint32_t)(4 + body));
             nblk++;
         }
-        if (nblk) {
-            b.out_len.resize(nblk);
-            int rc = b.out.reserve((size_t)nblk * bsz) ? 0 : -1;
-            if (rc == 0) rc = plz4cu_decompress_batch_host(b.recs.p, b.recs_len, b.rec_off.data(), nullptr, nblk, (uint32_t)bsz, blk_check, 0,
-                                                           dict, b.out.p, (uint64_t)bsz, b.out_len.data());
-            if (rc < 0) { nblk = 0; b.tail_event = PLZ4CU_Z_ENGINE; }
-        }
         b.nblk = nblk;
-        if (verify_content_hash) {
-            // the serial checksum of the decoded bytes, in stream order, stops at the first block that failed
-            auto job = [this, &b] {
-                for (uint32_t i = 0; i < b.nblk && b.out_len[i] >= 0; i++) hasher.update(b.out.p + (size_t)i * bsz, (size_t)b.out_len[i]);
-                b.digest = hasher.digest();
-            };
-            // small batches are hashed in place (in order: the hash thread, if it ever started, is idle first)
-            if (async && (size_t)b.nblk * bsz >= (1u << 20)) b.hash_ticket = hash_q.submit(job);
-            else { hash_q.drain(); job(); }
-        }
+    }
+    // one engine call for the batch (the slot's engine thread when async)
+    void decode_records(Batch& b)
+    {
+        if (b.nblk == 0) return;
+        b.out_len.resize(b.nblk);
+        int rc = b.out.reserve((size_t)b.nblk * bsz) ? 0 : -1;
+        if (rc == 0) rc = plz4cu_decompress_batch_host(b.recs.p, b.recs_len, b.rec_off.data(), nullptr, b.nblk, (uint32_t)bsz, blk_check, 0,
+                                                       dict, b.out.p, (uint64_t)bsz, b.out_len.data());
+        if (rc < 0) { b.nblk = 0; b.tail_event = PLZ4CU_Z_ENGINE; }
+    }
+    // the serial checksum of the decoded bytes, in stream order, stops at the first block that failed; submitted by the
+    // caller's thread when it starts on the batch, so the jobs line up in batch order whatever order decodes finish in
+    void hash_batch(Batch& b)
+    {
+        if (!verify_content_hash) return;
+        auto job = [this, &b] {
+            for (uint32_t i = 0; i < b.nblk && b.out_len[i] >= 0; i++) hasher.update(b.out.p + (size_t)i * bsz, (size_t)b.out_len[i]);
+            b.digest = hasher.digest();
+        };
+        // small batches are hashed in place (in order: the hash thread, if it ever started, is idle first)
+        if (async && (size_t)b.nblk * bsz >= (1u << 20)) b.hash_ticket = hash_q.submit(job);
+        else { hash_q.drain(); job(); }
     }
     size_t next_fill_bytes()
     {
@@ -827,33 +850,85 @@ struct plz4cu_reader {
         next_batch_bytes = std::min(limit, next_batch_bytes * 4);
         return want;
     }
-    // make the next batch current; while the frame body goes on, one more is read and decoded ahead on the engine
-    // thread.  The first batch of a body is filled on the caller's thread (it is waited for anyway), so a stream
-    // that fits one batch never starts a thread.
+    // batches decoding ahead of the caller: one for small blocks (a batch fills the GPU), more for large ones
+    int read_ahead_depth() const { return bsz >= (1 << 20) ? kSlots - 1 : 1; }
+    // source thread: read batch after batch in order, hand each to its slot's engine thread, stay at most
+    // read_ahead_depth() batches ahead of the caller; ends with the batch that carries the body's tail event
+    void source_loop()
+    {
+        cudaSetDevice(device);
+        for (;;) {
+            uint64_t k;
+            {
+                std::unique_lock<std::mutex> lk(ring_mu);
+                ring_cv.wait(lk, [&] { return stop_source || produced - released <= (uint64_t)read_ahead_depth(); });
+                if (stop_source) { source_done = true; ring_cv.notify_all(); return; }
+                k = produced;
+            }
+            Batch& b = bt[k % kSlots];
+            if (b.hash_ticket) hash_q.wait(b.hash_ticket);      // the previous tenant of these buffers may still be hashed
+            read_records(b, next_fill_bytes());
+            const bool last = b.tail_event != 0;
+            if (b.nblk) b.ticket = engine_q[k % kSlots].submit([this, &b] { cudaSetDevice(device); decode_records(b); });
+            {
+                std::lock_guard<std::mutex> lk(ring_mu);
+                produced = k + 1;
+                if (last) source_done = true;
+            }
+            ring_cv.notify_all();
+            if (last) return;
+        }
+    }
+    // make the next batch current.  With small blocks the first batch of a body is read and decoded on the caller's
+    // thread (it is waited for anyway), so a stream that fits one batch never starts a thread; if the body goes on, the
+    // source loop takes over.  With large blocks the loop starts at once: one block alone takes tens of milliseconds
+    // to decode, and the batches behind the first should be decoding during that time.
     void advance_batch()
     {
-        if (prefetched) {
-            cb ^= 1;
-            prefetched = false;
-            engine_q.wait(bt[cb].ticket);
+        uint64_t next = have_batch ? cb_index + 1 : 0;
+        if (!async) {
+            // synchronous flavour: one slot, refilled in place
+            read_records(bt[0], next_fill_bytes());
+            decode_records(bt[0]);
+            next = 0;
+        } else if (!have_batch && read_ahead_depth() == 1) {
+            Batch& b = bt[0];
+            if (b.hash_ticket) hash_q.wait(b.hash_ticket);
+            read_records(b, next_fill_bytes());
+            decode_records(b);
+            produced = 1; released = 0;
+            source_done = b.tail_event != 0;
+            if (!source_done) source_q.submit([this] { source_loop(); });
         } else {
-            fill_batch(bt[cb], next_fill_bytes());
+            if (!have_batch) {
+                produced = 0; released = 0;
+                source_done = false;
+                source_q.submit([this] { source_loop(); });
+            }
+            bool there;
+            {
+                std::unique_lock<std::mutex> lk(ring_mu);
+                released = next;                                // everything before `next` may be overwritten
+                ring_cv.notify_all();
+                ring_cv.wait(lk, [&] { return produced > next || source_done; });
+                there = produced > next;
+            }
+            Batch& b = bt[next % kSlots];
+            if (there) engine_q[next % kSlots].wait(b.ticket);
+            else { b.nblk = 0; b.tail_event = PLZ4CU_Z_ENGINE; }         // the source loop stopped short: cannot happen while reading
         }
+        cb_index = next;
+        have_batch = true;
         cur = 0;
-        if (async && bt[cb].tail_event == 0 && bt[cb].nblk > 0) {
-            Batch& nb = bt[cb ^ 1];
-            const size_t want = next_fill_bytes();
-            nb.ticket = engine_q.submit([this, &nb, want] { cudaSetDevice(device); fill_batch(nb, want); });
-            prefetched = true;
-        }
+        hash_batch(cbatch());
     }
 
     // rdr/rdr.go:207-227 nextBlock: 0 = a block is current, 2 = EndMark, <0 error
     int next_block()
     {
         have_block = false;
-        if (cur >= bt[cb].nblk && bt[cb].tail_event == 0) advance_batch();
-        Batch& b = bt[cb];
+        if (!have_batch || (cur >= cbatch().nblk && cbatch().tail_event == 0)) advance_batch();
+        Batch& b = cbatch();
         if (opt.o.progress) opt.o.progress(opt.o.progress_ctx, src_pos, dst_pos);
         if (cur < b.nblk) {
             const int32_t r = b.out_len[cur];
@@ -892,7 +967,7 @@ struct plz4cu_reader {
         src_pos += b.tail_read;
         return ev;
     }
-    const uint8_t* block_ptr() const { return bt[cb].out.p + (size_t)run_first * bsz; }
+    const uint8_t* block_ptr() { return cbatch().out.p + (size_t)run_first * bsz; }
 
     // rdr/rdr.go:91-101
     int handle_end_mark()
