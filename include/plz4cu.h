@@ -271,7 +271,7 @@ typedef struct plz4cu_opts {
     int32_t  level;              /* WithLevel: only 1 is implemented by this engine                       */
     int32_t  n_parallel;         /* WithParallel: 0 = synchronous, one block per engine call; != 0 = staged */
     int32_t  pending_size;       /* WithPendingSize: bytes of blocks per engine call (<= 0: auto, 64 MiB;   */
-                                 /*   readers of >= 1 MiB blocks: 128 MiB, up to 7 batches decoding ahead)   */
+                                 /*   128 MiB for >= 1 MiB blocks, readers then keep up to 7 batches decoding) */
     int32_t  block_size_idx;     /* WithBlockSize: 4..7 (64 KiB, 256 KiB, 1 MiB, 4 MiB)                    */
     int32_t  block_checksum;     /* WithBlockChecksum                                                      */
     int32_t  content_checksum;   /* WithContentChecksum                                                    */

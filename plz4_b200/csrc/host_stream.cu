@@ -270,6 +270,7 @@ struct Opts {
         size_t want = kAutoBatchMin;
         if (o.pending_size > 0) want = (size_t)o.pending_size;
         else if (decode) want = std::min(kAutoBatchMax, std::max(kAutoBatchMin, kAutoBatchBlocks * (size_t)bsz));
+        else if (bsz >= (1 << 20)) want = 2 * kAutoBatchMin;   // fragments + stitch cost a few ms per call whatever its size
         want = std::max<size_t>(want, (size_t)bsz);
         return want / bsz * bsz;
     }
