@@ -30,6 +30,7 @@
 namespace plz4 {
 
 constexpr int kEncodeWarps = 4;                 // blocks per CTA
+constexpr int kLongLiterals = 64;               // literal runs from this length on are copied by the whole warp
 constexpr int kQueueLen = 48;                   // sequences queued per warp: 32 to flush + the <= 8 a group can add
 
 // Table geometry.  The 12-bit table uses 7/8 of its 4096 slots: 3584 x u16 = 7 KiB per warp, which lets a seventh
@@ -104,11 +105,19 @@ __device__ __noinline__ int flush_queue(const uint4* queue, int cnt, const uint8
         *o++ = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (ml < 15 ? ml : 15));
         if (le) { int r = lit - 15; for (; r >= 255; r -= 255) *o++ = 255; *o++ = (uint8_t)r; }
         const uint8_t* lp = src + (int)e.x;
-        for (int j = 0; j < lit; j++) o[j] = lp[j];
+        if (lit < kLongLiterals) for (int j = 0; j < lit; j++) o[j] = lp[j];
         o += lit;
         o[0] = (uint8_t)e.w; o[1] = (uint8_t)(e.w >> 8);
         o += 2;
         if (me) { int r = ml - 15; for (; r >= 255; r -= 255) *o++ = 255; *o++ = (uint8_t)r; }
+    }
+    // long literal runs (poorly compressible stretches) are copied by the whole warp, one run after the other,
+    // instead of byte by byte by the lane that owns the sequence
+    for (uint32_t todo = __ballot_sync(FULL_MASK, mine && lit >= kLongLiterals); todo; todo &= todo - 1) {
+        const int l = __ffs(todo) - 1;
+        const int from = (int)__shfl_sync(FULL_MASK, e.x, l), n = __shfl_sync(FULL_MASK, lit, l);
+        const int at = __shfl_sync(FULL_MASK, incl - size + 1 + le, l);
+        warp_copy(out + at, src + from, (uint32_t)n, lane);
     }
     return total;
 }
