@@ -142,6 +142,7 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                                                 uint8_t* ring)
 {
     constexpr int kBatchBytes = 1024;               // output bytes one batch may span (32 bitmap words)
+    constexpr int kMaxBatchLit = 63;                // longest literal run a batched sequence may carry (6 bits)
     if (cap == 0) return (n == 1 && src[0] == 0) ? 0 : -1;
     if (n == 0) return -1;
 
@@ -169,12 +170,16 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
             const uint32_t w0 = a0 >> 2;                        // first window word
             const uint32_t widx = w0 + (uint32_t)lane;
             const uint32_t w = (widx <= last4) ? src4[widx] : 0u;
-            // header length if a token started at each of my 4 bytes (3 + literals, + 1 if the match nibble is 15)
+            // header length if a token started at each of my 4 bytes: 3 + literals, + 1 if the match nibble is 15; a
+            // literal nibble of 15 takes its extension from the byte after the token (one extension byte only)
+            const uint32_t wn = __shfl_down_sync(FULL_MASK, w, 1);       // lane 31 gets junk: tokens there end the batch
             uint32_t dpack = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const uint32_t tok = (w >> (8 * i)) & 0xFFu;
-                const uint32_t dl = 3u + (tok >> 4) + ((tok & 15u) == 15u ? 1u : 0u);
+                const uint32_t nxt = (i < 3 ? (w >> (8 * i + 8)) : wn) & 0xFFu;
+                uint32_t dl = 3u + (tok >> 4) + ((tok & 15u) == 15u ? 1u : 0u);
+                if ((tok >> 4) == 15u) dl = min(dl + 1u + nxt, 255u);
                 dpack |= dl << (8 * i);
             }
             // walk the chain through shared memory (one byte load per sequence): qb = byte offset inside the window
@@ -194,21 +199,28 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                 return (__shfl_sync(FULL_MASK, w, bo >> 2) >> ((bo & 3u) * 8u)) & 0xFFu;
             };
             const uint32_t tok = wbyte(myq);
+            const uint32_t lext = wbyte(min(myq + 1u, 127u));
             const uint32_t L = tok >> 4, M = tok & 15u;
-            const uint32_t ob = myq + 1u + (L < 15u ? L : 0u);  // window offset of the match offset
+            const bool longlit = L == 15u;                      // literal run of 15 + one extension byte (lz4.c:2121-2128)
+            const uint32_t lit = longlit ? 15u + lext : L;
+            const uint32_t lp = myq + (longlit ? 2u : 1u);      // window offset of the first literal
+            const bool inwin = lit <= (uint32_t)kMaxBatchLit && lp + lit + 2u < 128u;
+            const uint32_t ob = inwin ? lp + lit : 0u;          // window offset of the match offset
             const uint32_t off = wbyte(ob) | (wbyte(ob + 1u) << 8);
             const uint32_t ext = wbyte(ob + 2u);
             const int pos = ip + (int)(myq - (a0 & 3u));        // position of my token in src
-            const int ip1 = pos + 1;
-            const int ipn = ip1 + (int)L + 2 + (M == 15u ? 1 : 0);
-            const bool good = lane < nseq && L != 15u && ip1 < n - 16 &&
+            const int ip1 = pos + (longlit ? 2 : 1);            // first literal
+            const int ipn = ip1 + (int)lit + 2 + (M == 15u ? 1 : 0);
+            // a long literal run is no shortcut sequence: it must pass liblz4's general-path test on the input side
+            // (lz4.c:2279: ip + length <= iend - (2 + 1 + LASTLITERALS)); the output side is tested with the positions
+            const bool good = lane < nseq && inwin && pos + 1 < n - 16 && (!longlit || (lext != 255u && ip1 + (int)lit <= n - 8)) &&
                               (M != 15u || (ext != 255u && ipn <= n - LASTLITERALS + 1));
             const uint32_t badseq = __ballot_sync(FULL_MASK, lane < nseq && !good);
             if (badseq) nseq = __ffs(badseq) - 1;               // decode_one takes the first one that does not fit
-            my_lit = (int)L; my_litpos = ip1; my_off = off;
+            my_lit = (int)lit; my_litpos = ip1; my_off = off;
             my_mlen = (int)M + MINMATCH + (M == 15u ? (int)ext : 0);
             my_ipn = ipn;
-            my_simple = (M != 15u) && off >= 8u;
+            my_simple = !longlit && (M != 15u) && off >= 8u;
         }
 
         if (nseq > 0) {
@@ -224,7 +236,9 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
             const int m = o + my_lit;                           // where my match starts
             // a sequence is a shortcut only while op <= cap-32 (output side); the start bitmap below covers 1024 output
             // bytes: cut the batch at the first sequence that breaks either limit
-            const uint32_t late = __ballot_sync(FULL_MASK, lane < nseq && (o > cap - 32 || o + span - op > kBatchBytes));
+            // ... and a long literal run must end MFLIMIT short of the capacity (lz4.c:2279: cpy <= oend - MFLIMIT)
+            const uint32_t late = __ballot_sync(FULL_MASK, lane < nseq && (o > cap - 32 || o + span - op > kBatchBytes ||
+                                                                            (my_lit >= 15 && m > cap - MFLIMIT)));
             if (late) nseq = __ffs(late) - 1;
             if (nseq > 0) {
                 const bool mine = lane < nseq;
@@ -245,7 +259,7 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                 __syncwarp();
                 const uint32_t my_bits = bitmap[lane];
                 // everything a byte needs to know about its sequence, in two words
-                const uint32_t packA = (uint32_t)(orel & 0x7FF) | ((uint32_t)my_lit << 11) | (my_off << 15);
+                const uint32_t packA = (uint32_t)(orel & 0x3FF) | ((uint32_t)my_lit << 10) | (my_off << 16);
                 uint8_t* dx = dst + out0 + lane;
                 int j = 0;
                 for (int c = 0; c < out1 - out0; c += 32, j++, dx += 32) {
@@ -256,9 +270,9 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                     const uint32_t ka = __shfl_sync(FULL_MASK, packA, k);
                     const int kp = __shfl_sync(FULL_MASK, my_litpos, k);
                     const bool live = xr < out1 - out0;
-                    const int d = xr - (int)(ka & 0x7FFu);                                          // byte index inside the sequence
-                    const bool is_lit = d < (int)((ka >> 11) & 15u);
-                    const int sr = xr - (int)(ka >> 15);                                            // match source, relative to out0
+                    const int d = xr - (int)(ka & 0x3FFu);                                          // byte index inside the sequence
+                    const bool is_lit = d < (int)((ka >> 10) & 63u);
+                    const int sr = xr - (int)(ka >> 16);                                            // match source, relative to out0
                     const bool fwd = live && !is_lit && sr >= c;                                    // source inside this chunk
                     uint32_t val = 0;
                     if (live && !fwd) {
