@@ -86,6 +86,55 @@ def test_corrupted_streams_same_codes(gpu, port, codec):
                 assert rw == want
 
 
+def _litruns(rng, n):
+    """random literal runs of 10..90 bytes separated by copies of earlier data: tokens with literal nibble 15"""
+    out = bytearray()
+    while len(out) < n:
+        out += rng.randbytes(rng.randint(10, 90))
+        if len(out) > 40:
+            k = rng.randint(4, 40)
+            s = rng.randrange(0, len(out) - k)
+            out += out[s:s + k]
+    return bytes(out[:n])
+
+
+def test_long_literal_runs_same_codes(gpu, port, codec):
+    """Sequences with a literal-length extension byte go through the batched path: exact lengths, bytes and error
+    codes against liblz4 on intact, truncated and mutated streams, at exact and tight capacities."""
+    rng = random.Random(1234)
+    cases = []
+    for it in range(1500):
+        n = rng.choice([60, 200, 1000, 5000, 20000, 70000])
+        data = _litruns(rng, n)
+        c = bytearray(codec.compress(data))
+        m = rng.randrange(6)
+        if m == 0:
+            for _ in range(rng.randint(1, 3)):
+                c[rng.randrange(len(c))] = rng.getrandbits(8)
+        elif m == 1:
+            c = c[: rng.randrange(1, len(c) + 1)]
+        elif m == 2:
+            c[rng.randrange(len(c))] = rng.choice([0xFF, 0xF0, 0xF4, 0x0F, 0x00])
+        elif m == 3:
+            i = rng.randrange(len(c)); c[i:i] = rng.randbytes(rng.randint(1, 3))
+        cases.append((bytes(c), n + rng.choice([0, 0, 5, 11, 12, 13, 31, 32, 33, 100]) - rng.choice([0, 0, 0, 1, 7])))
+    for group_cap in sorted({c[1] for c in cases}):
+        grp = [c[0] for c in cases if c[1] == group_cap]
+        buf, off = b"".join(grp), np.cumsum([0] + [len(c) for c in grp])[:-1]
+        out, res = gpu.decompress_batch(buf, off, group_cap, raw_len=[len(c) for c in grp])
+        hits = port.lib.orc_dbg_zero_offset_hits
+        hits.restype = __import__("ctypes").c_uint64
+        for i, c in enumerate(grp):
+            z = hits()
+            want, data = port.decompress(c, group_cap)
+            assert res[i] == want, (c.hex()[:200], group_cap, res[i], want)
+            if want >= 0:
+                assert out[i, :want].tobytes() == data
+            elif hits() == z:
+                rw, _ = codec.decompress(c, group_cap)
+                assert rw == want
+
+
 def test_frame_records_checksum_stored_overflow(gpu, port):
     bsz = 65536
     blocks = [make("log", bsz), make("random", bsz), make("zeros", bsz), make("words", 777), make("random", 100), b"hello"]
