@@ -162,7 +162,9 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
         // dependent loads.  Headers that do not fit the simple shape (literal nibble 15, more than one length
         // byte, too close to the end of the input) end the batch and go through decode_one.
         int nseq = 0;
-        int my_lit = 0, my_litpos = 0, my_mlen = 0, my_ipn = 0;
+        int my_lit = 0, my_litpos = 0, my_mlen = 0;
+        // input position after my sequence: literals, offset, and the one extension byte a match nibble of 15 carries
+        auto my_ipn = [&]() { return my_litpos + my_lit + 2 + (my_mlen >= MINMATCH + 15 ? 1 : 0); };
         uint32_t my_off = 0;
         bool my_simple = false;                     // second shortcut stage applies on the input side (nibble != 15, offset >= 8)
         {
@@ -219,7 +221,6 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
             if (badseq) nseq = __ffs(badseq) - 1;               // decode_one takes the first one that does not fit
             my_lit = (int)lit; my_litpos = ip1; my_off = off;
             my_mlen = (int)M + MINMATCH + (M == 15u ? (int)ext : 0);
-            my_ipn = ipn;
             my_simple = !longlit && (M != 15u) && off >= 8u;
         }
 
@@ -246,7 +247,7 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                 const bool bad = mine && !stage2 &&
                                  ((check_offset && m - (int)my_off + dsz < 0) || my_off == 0 || m + my_mlen > cap - LASTLITERALS);
                 const uint32_t badmask = __ballot_sync(FULL_MASK, bad);
-                if (badmask) return -__shfl_sync(FULL_MASK, my_ipn, __ffs(badmask) - 1) - 1;
+                if (badmask) return -__shfl_sync(FULL_MASK, my_ipn(), __ffs(badmask) - 1) - 1;
 
                 // ---- 3. copy: 32 output bytes per step, one per lane
                 const int out0 = op;
@@ -294,7 +295,7 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                     }
                     __syncwarp();
                 }
-                ip = __shfl_sync(FULL_MASK, my_ipn, nseq - 1);
+                ip = __shfl_sync(FULL_MASK, my_ipn(), nseq - 1);
                 op = out1;
                 continue;
             }
