@@ -143,3 +143,25 @@ def test_compress_frame_device_equals_the_host_writer(gpu, port, mixed):
     out, info = gpu.decompress_frame_device(frame, dict=dct)
     assert torch.equal(out, d[: 3 * MiB]) and info.dict_id == 5
     assert F.read_frames(bytes(frame.cpu().numpy()), port, dictionary=mixed[:65536]) == data[: 3 * MiB]
+
+
+def test_frame_index_edges(gpu, mixed):
+    from plz4_b200 import _lib
+    L = _lib.lib()
+    frame = compress(gpu, mixed[:2 * MiB + 5], block_size_idx=4, block_checksum=False, content_checksum=False)
+    d = dev(frame)
+    nblk = 33
+    rec_off = torch.zeros(64, dtype=torch.int64, device="cuda")
+    n, end = C.c_uint64(), C.c_uint64()
+    call = lambda ln, cap: L.plz4cu_frame_index_device(None, C.c_void_p(d.data_ptr() + 7), ln, 65536, 0, C.c_void_p(rec_off.data_ptr()),
+                                                       cap, C.byref(n), C.byref(end))
+    assert call(len(frame) - 7, 64) == 0 and n.value == nblk and end.value == len(frame) - 7
+    assert call(len(frame) - 7, 3) == _lib.ERR_ARG and n.value == nblk          # too little room: the count still comes back
+    assert call(3, 64) == -109 and n.value == 0                                  # ErrBlockSizeRead: not even a size word
+    assert call(len(frame) - 7 - 4, 64) == -109 and n.value == nblk              # EndMark cut off
+    assert call(len(frame) - 7 - 6, 64) == -110 and n.value == nblk - 1          # last record cut short: ErrBlockRead
+    # whole-frame call on truncated headers
+    for cut in (0, 3, 6):
+        with pytest.raises(gpu.StreamError) as e:
+            gpu.decompress_frame_device(dev(frame[:cut] + b"\\0" * (1 if cut == 0 else 0)))
+        assert e.value.name in ("ErrHeaderRead", "ErrMagic")

@@ -239,3 +239,25 @@ def test_bad_seeker_and_early_close(gpu, big):
     give_up_early()
     gc.collect()
     assert L.plz4cu_host_outstanding() == before
+
+
+def test_flush_storm_after_the_stream_went_threaded(gpu, port, big):
+    """wr_test.go:238-346 on a stream that already runs its helper threads: every Flush is a barrier and makes a block."""
+    dst = io.BytesIO()
+    w = gpu.NewWriter(dst, block_size_idx=4, block_checksum=True, content_checksum=True, pending_size=12 * MiB)
+    w.write(big[:30 * MiB])                                              # slabs rotate, engine / sink / hash threads run
+    pos = 30 * MiB
+    sizes = []
+    for i in range(40):
+        n = 1 + (i * 7919) % 3000
+        w.write(big[pos:pos + n]); pos += n
+        w.flush()
+        sizes.append(len(dst.getvalue()))
+        w.flush()                                                        # nothing pending: no empty block
+        assert len(dst.getvalue()) == sizes[-1]
+    w.write(big[pos:])
+    w.close()
+    assert all(b > a for a, b in zip(sizes, sizes[1:]))
+    f = dst.getvalue()
+    assert F.read_frames(f, port) == big
+    assert decompress(gpu, f, pending_size=12 * MiB) == big
