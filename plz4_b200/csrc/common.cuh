@@ -92,44 +92,16 @@ constexpr uint32_t XP1 = 2654435761u, XP2 = 2246822519u, XP3 = 3266489917u, XP4 
 
 __device__ __forceinline__ uint32_t rol32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
 
-// xxh32.ChecksumZero (xxh32/xxh32zero.go:238-280) of p[0..n) computed by one warp; every lane
-// returns the digest.  The four accumulator chains are inherently serial along the stripes, so
-// lanes 0..3 carry them; the other lanes only help to fetch: a chunk of 32 stripes (512 B) is
-// loaded coalesced (4 words per lane) and handed to the chain lanes with shuffles.
-__device__ __forceinline__ uint32_t warp_xxh32(const uint8_t* p, uint32_t n, int lane)
+// The four accumulators live in lanes j = lane & 3 (every group of four lanes carries a copy).
+__device__ __forceinline__ uint32_t xxh32_init(int lane)
 {
-    uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-    const uint32_t sh = (uint32_t)(a & 3) * 8;
-    const uint32_t nstripes = n >> 4;
-    const uint32_t nwords = nstripes << 2;
-    uint32_t acc;
-    {
-        int j = lane & 3;
-        acc = (j == 0) ? (XP1 + XP2) : (j == 1) ? XP2 : (j == 2) ? 0u : (0u - XP1);
-    }
-    for (uint32_t base = 0; base < nstripes; base += 32) {
-        uint32_t w[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            uint32_t idx = base * 4 + r * 32 + lane;
-            uint32_t v = 0;
-            if (idx < nwords) {
-                v = wp[idx];
-                if (sh) v = __funnelshift_r(v, wp[idx + 1], sh);
-            }
-            w[r] = v;
-        }
-        uint32_t left = nstripes - base;      // stripes in this chunk (warp-uniform)
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                uint32_t x = __shfl_sync(FULL_MASK, w[r], 4 * t + (lane & 3));
-                if ((uint32_t)(r * 8 + t) < left) acc = rol32(acc + x * XP2, 13) * XP1;
-            }
-        }
-    }
+    const int j = lane & 3;
+    return (j == 0) ? (XP1 + XP2) : (j == 1) ? XP2 : (j == 2) ? 0u : (0u - XP1);
+}
+
+// Merge of the accumulators, the 0..15 trailing bytes of p[0..n) and the avalanche (xxh32zero.go:259-277).
+__device__ __forceinline__ uint32_t xxh32_finish(uint32_t acc, const uint8_t* p, uint32_t n)
+{
     uint32_t h;
     if (n >= 16) {
         uint32_t v0 = __shfl_sync(FULL_MASK, acc, 0), v1 = __shfl_sync(FULL_MASK, acc, 1);
@@ -139,7 +111,7 @@ __device__ __forceinline__ uint32_t warp_xxh32(const uint8_t* p, uint32_t n, int
         h = XP5;
     }
     h += n;
-    uint32_t i = nstripes << 4;
+    uint32_t i = (n >> 4) << 4;
     for (; i + 4 <= n; i += 4) {
         uint32_t v = (uint32_t)p[i] | ((uint32_t)p[i + 1] << 8) | ((uint32_t)p[i + 2] << 16) | ((uint32_t)p[i + 3] << 24);
         h = rol32(h + v * XP3, 17) * XP4;
@@ -147,6 +119,98 @@ __device__ __forceinline__ uint32_t warp_xxh32(const uint8_t* p, uint32_t n, int
     for (; i < n; i++) h = rol32(h + (uint32_t)p[i] * XP5, 11) * XP1;
     h ^= h >> 15; h *= XP2; h ^= h >> 13; h *= XP3; h ^= h >> 16;
     return h;
+}
+
+// `nstripes` whole stripes from word-aligned memory that answers quickly (a shared-memory tile): the chain only.
+__device__ __forceinline__ uint32_t xxh32_consume_words(uint32_t acc, const uint32_t* w, uint32_t nstripes, int lane)
+{
+    const uint32_t nwords = nstripes << 2;
+    for (uint32_t base = 0; base < nstripes; base += 32) {
+        uint32_t y[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t idx = base * 4 + r * 32 + lane;
+            y[r] = (idx < nwords ? w[idx] : 0u) * XP2;
+        }
+        const uint32_t left = nstripes - base;
+        if (left >= 32) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+#pragma unroll
+                for (int t = 0; t < 8; t++) acc = rol32(acc + __shfl_sync(FULL_MASK, y[r], 4 * t + (lane & 3)), 13) * XP1;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    const uint32_t x = __shfl_sync(FULL_MASK, y[r], 4 * t + (lane & 3));
+                    if ((uint32_t)(r * 8 + t) < left) acc = rol32(acc + x, 13) * XP1;
+                }
+            }
+        }
+    }
+    return acc;
+}
+
+// xxh32.ChecksumZero (xxh32/xxh32zero.go:238-280) of p[0..n) computed by one warp; every lane
+// returns the digest.  The four accumulator chains are inherently serial along the stripes, so
+// lanes 0..3 carry them; the other lanes only help to fetch: a chunk of 32 stripes (512 B) is
+// loaded coalesced (4 words per lane) and handed to the chain lanes with shuffles.
+static __device__ __noinline__ uint32_t warp_xxh32(const uint8_t* p, uint32_t n, int lane)
+{
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t nstripes = n >> 4;
+    const uint32_t nwords = nstripes << 2;
+    uint32_t acc = xxh32_init(lane);
+    // one chunk = 32 stripes = 4 words per lane, already multiplied by XP2 (that product is off the serial chain)
+    auto load_chunk = [&](uint32_t base, uint32_t (&y)[4]) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t idx = base * 4 + r * 32 + lane;
+            uint32_t v = 0;
+            if (idx < nwords) {
+                v = wp[idx];
+                if (sh) v = __funnelshift_r(v, wp[idx + 1], sh);
+            }
+            y[r] = v * XP2;
+        }
+    };
+    uint32_t cur[4] = {0, 0, 0, 0};
+    if (nstripes) load_chunk(0, cur);
+    for (uint32_t base = 0; base < nstripes; base += 32) {
+        // the next chunk's loads are in flight while this one goes down the chain, and the lines eight chunks
+        // further on are asked into L1: one chunk of chain work is far shorter than a trip to HBM
+        uint32_t nxt[4] = {0, 0, 0, 0};
+        if (base + 32 < nstripes) load_chunk(base + 32, nxt);
+        {
+            const uint32_t ahead = (base + 32 * 8) * 4 + (uint32_t)lane * 4;
+            if (ahead < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + ahead));
+        }
+        const uint32_t left = nstripes - base;      // stripes in this chunk (warp-uniform)
+        if (left >= 32) {
+            // full chunk: nothing but add, rotate, multiply on the chain; the shuffles do not depend on it
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+#pragma unroll
+                for (int t = 0; t < 8; t++) acc = rol32(acc + __shfl_sync(FULL_MASK, cur[r], 4 * t + (lane & 3)), 13) * XP1;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    const uint32_t x = __shfl_sync(FULL_MASK, cur[r], 4 * t + (lane & 3));
+                    if ((uint32_t)(r * 8 + t) < left) acc = rol32(acc + x, 13) * XP1;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) cur[r] = nxt[r];
+    }
+    return xxh32_finish(acc, p, n);
 }
 
 __device__ __forceinline__ void store_le32(uint8_t* p, uint32_t v)

@@ -411,6 +411,7 @@ lz4_compress_kernel(EncodeArgs a)
 // the fragment streams into one LZ4 block: the literals left over at the end of fragment k become part of the first
 // sequence of fragment k+1, so only that sequence's token / length bytes are rewritten; everything else is copied.
 constexpr int kFragBytes = 65536;
+constexpr int kHashTileWords = 4096;            // 16 KiB tiles of payload staged in shared memory for the block checksum
 
 struct FragArgs {
     EncodeArgs e;
@@ -459,7 +460,7 @@ lz4_stitch_kernel(FragArgs a)
     __shared__ int s_out[kMaxFrags];              // output offset of the fragment's (rewritten) first token; -1 = skip
     __shared__ int s_carry[kMaxFrags];            // literals carried into the fragment
     __shared__ int s_pos[kMaxFrags];              // source position of the fragment
-    __shared__ int s_end, s_tail, s_ok;
+    __shared__ int s_end, s_tail, s_ok, s_c;
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const uint32_t b = blockIdx.x;
@@ -520,7 +521,7 @@ lz4_stitch_kernel(FragArgs a)
         }
     }
     __syncthreads();
-    if (warp != 0) return;
+    if (warp == 0) {
     int c = 0;
     if (s_ok) {
         // last literals of the block (lz4.c:1302-1329)
@@ -532,8 +533,53 @@ lz4_stitch_kernel(FragArgs a)
         warp_copy(out + op, src + n_blk - carry, (uint32_t)carry, lane);
         c = op + carry;
     }
-    __threadfence_block();
-    finish_record(a.e, b, src, n_blk, rec, out, c, lane);
+    // ---- record framing (blk/blk.go:78-106) by the whole CTA: a block of this size is too much for one warp
+    if (lane == 0) s_c = c;
+    }
+    __syncthreads();
+    int c = s_c;
+    if (a.e.raw_blocks) {
+        if (threadIdx.x == 0) a.e.rec_len[b] = (uint32_t)c;              // 0 = does not fit
+        return;
+    }
+    uint32_t word = (uint32_t)c;
+    if (c == 0) {                                                        // blk/blk.go:78-92: store raw
+        const int per = ((n_blk + kStitchWarps - 1) / kStitchWarps + 15) & ~15;
+        const int lo = min(n_blk, warp * per), hi = min(n_blk, lo + per);
+        warp_copy(out + lo, src + lo, (uint32_t)(hi - lo), lane);
+        c = n_blk;
+        word = (uint32_t)n_blk | 0x80000000u;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_le32(rec, word);
+    uint32_t total = 4u + (uint32_t)c;
+    if (a.e.block_checksum) {                                            // blk/blk.go:98-102
+        // xxh32 is serial along the payload, so one warp carries the chain; the other warps keep it fed: they copy
+        // the payload tile by tile into shared memory (two tiles, one being filled while the other is hashed), which
+        // turns every load the chain waits for from a trip to L2 / HBM into a shared-memory access
+        __shared__ uint32_t s_tile[2][kHashTileWords];
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(out);     // payload is 4-byte aligned (slot base + 4)
+        const uint32_t nstripes = (uint32_t)c >> 4;
+        const uint32_t ntiles = (nstripes * 4 + kHashTileWords - 1) / kHashTileWords;
+        auto fill = [&](uint32_t t) {
+            const uint32_t w0 = t * kHashTileWords, w1 = min(nstripes * 4, w0 + kHashTileWords);
+            for (uint32_t i = w0 + (threadIdx.x - 32); i < w1; i += (kStitchWarps - 1) * 32) s_tile[t & 1][i - w0] = pw[i];
+        };
+        uint32_t acc = xxh32_init(lane);
+        if (warp != 0 && ntiles) fill(0);
+        __syncthreads();
+        for (uint32_t t = 0; t < ntiles; t++) {
+            if (warp != 0) { if (t + 1 < ntiles) fill(t + 1); }
+            else acc = xxh32_consume_words(acc, s_tile[t & 1], min((uint32_t)kHashTileWords / 4, nstripes - t * (kHashTileWords / 4)), lane);
+            __syncthreads();
+        }
+        if (warp == 0) {
+            const uint32_t x = xxh32_finish(acc, out, (uint32_t)c);
+            if (lane == 0) store_le32(out + c, x);
+        }
+        total += 4;
+    }
+    if (threadIdx.x == 0) a.e.rec_len[b] = total;
 }
 
 // Dictionary table: for every hash the LAST dictionary position holding it (what a block would have seen
