@@ -54,6 +54,11 @@ class ClockSampler:
         self.idx = gpu_index
         self.rows = []
         self.proc = None
+        self.n0 = 0
+
+    def mark(self):
+        """The timed region starts here: only samples taken from now on are reported."""
+        self.n0 = len(self.rows)
 
     def start(self):
         try:
@@ -77,17 +82,24 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        rows = self.rows[self.n0:]
+        nearest = not rows and bool(self.rows)
+        if nearest:                      # region shorter than one sampling period: the rows right before it, under the same load
+            rows = self.rows[-2:]
+        sm = sorted(float(r[1]) for r in rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) < 9:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if nearest:
+            out["note"] = "timed region shorter than the sampling period: samples taken during the warm-up just before it"
+        return out
 
 
 # ------------------------------------------------------------------ CPU reference arm
@@ -229,6 +241,10 @@ def run_gpu(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi needs up to a second to deliver its first row on a multi-GPU box: start it before the warm-up and
+    # count only the rows that arrive inside the timed region (sampler.mark() below)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         compress()
         decompress()
@@ -238,11 +254,10 @@ def run_gpu(args) -> None:
     assert torch.equal(out, src), "round trip mismatch"
     csize = int(rec_len.to(torch.int64).sum())      # C' = framed compressed bytes (size word + payload + xxh32)
 
-    sampler = ClockSampler(local)
     launches0 = L.plz4cu_launch_count()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
-    sampler.start()
+    sampler.mark()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         ev[k][0].record(stream)
