@@ -48,6 +48,7 @@ extern "C" {
 
 #define PLZ4CU_E_BLOCKHASH   ((int32_t)-0x7F000001)
 #define PLZ4CU_E_OVERFLOW    ((int32_t)-0x7F000002)
+#define PLZ4CU_E_STALL       ((int32_t)-0x7F000003)   /* internal: a decode team's watchdog fired; never expected */
 
 #define PLZ4CU_STORED_BIT    0x80000000u
 #define PLZ4CU_REC_OVERHEAD  8u          /* size word + checksum, blk/pool.go:15 szOverhead */

@@ -26,6 +26,7 @@
 //      L1/L2 overlap instead of serialising.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace plz4 {
 
@@ -130,16 +131,74 @@ __device__ __noinline__ int decode_one(const uint8_t* __restrict__ src, int n, u
     return kStepMore;
 }
 
+// ---------------------------------------------------------------- team decode: shared state (one CTA per block)
+//
+// A launch with few, large blocks (plz4's default 4 MiB block: 64 blocks per 256 MiB) cannot be filled by one warp per
+// block, and a lone warp is bound by its own instruction latency.  The team kernel gives a block one CTA: warp 0 parses
+// (steps 1 and 2 below, unchanged, so accept/reject and return codes stay those of the one-warp decoder) and publishes
+// batches of up to 32 sequences into a ring of slots; kTeamCopyWarps warps produce the output, 32-byte chunk by chunk,
+// chunks dealt round-robin over the warps across batch boundaries.  A chunk waits only for the output bytes its own
+// matches read (`prog`: per warp, the output position below which all of that warp's chunks are complete), so chunks
+// whose sources lie further back than the chunks in flight proceed in parallel; literals never wait.  One more warp
+// checks the block checksum meanwhile.
+constexpr int kTeamCopyWarps = 7;
+constexpr int kTeamSlots = 8;                                   // batches published ahead of the slowest copy warp
+constexpr int kTeamThreads = (kTeamCopyWarps + 2) * 32;         // parser + copy warps + checksum warp
+constexpr int kTeamFar = 65536 - 16384;                         // matches reaching further back read global memory: the ring
+                                                                // slots behind them may already belong to chunks in flight
+                                                                // (kTeamSlots batches of <= 1 KiB)
+constexpr int kTeamSpinLimit = 1 << 25;                         // watchdog: a stalled team reports PLZ4CU_E_STALL, it never hangs
+
+struct TeamSlot {
+    uint32_t packA[32];            // per sequence: start relative to out0 (10 bits) | literals (6 bits) | offset (16 bits)
+    int litpos[32];                // per sequence: position of its first literal in the compressed block
+    uint32_t bits[32];             // bitmap of sequence starts over the batch's output range
+    int nseq, out0, out1, g0;      // g0: index of the batch's first chunk, modulo kTeamCopyWarps
+};
+
+struct TeamShared {
+    TeamSlot slot[kTeamSlots];
+    uint32_t window[32];                       // parser scratch (header lengths of the current window)
+    volatile int prog[kTeamCopyWarps];
+    volatile int passed[kTeamCopyWarps];       // batches a copy warp has left behind
+    volatile int head;                         // batches published
+    volatile int quit;                         // no batch will follow `head`
+    volatile int stall;                        // watchdog fired
+    volatile int hash_state;                   // 0 running, 1 checksum ok, 2 mismatch
+};
+
+// Spin until every copy warp's entry of `arr` has reached `need`.  The decision is a warp vote, so the warp stays converged.
+__device__ __forceinline__ bool team_wait(TeamShared* ts, const volatile int* arr, int need, int lane)
+{
+    for (int spins = 0;; spins++) {
+        const int v = lane < kTeamCopyWarps ? arr[lane] : 0x7FFFFFFF;
+        const int st = ts->stall;
+        if (__all_sync(FULL_MASK, v >= need)) break;
+        if (__any_sync(FULL_MASK, st != 0) || spins > kTeamSpinLimit) {
+            if (lane == 0) ts->stall = 1;
+            return false;
+        }
+    }
+    __threadfence_block();
+    return true;
+}
+// all copy warps have left batch `need - 1` behind
+__device__ __forceinline__ bool team_wait_passed(TeamShared* ts, int need, int lane) { return team_wait(ts, ts->passed, need, lane); }
+// every output byte below `need` has been written
+__device__ __forceinline__ bool team_wait_prog(TeamShared* ts, int need, int lane) { return team_wait(ts, ts->prog, need, lane); }
+
 // ---------------------------------------------------------------- batched decode
 
 // kRing: the last 64 KiB of output are mirrored in a shared-memory ring and match sources are read from there.
 // Used when a launch has too few blocks to hide global-memory latency with other warps (large block sizes):
 // the per-chunk round trip drops from an L2/HBM access to a shared-memory access.
-template <bool kDict, bool kRing>
+// kTeam: the caller is the parser warp of a team (see above): batches are published to the copy warps instead of being
+// copied here; decode_one still runs on this warp, after the copy warps have drained.
+template <bool kDict, bool kRing, bool kTeam = false>
 __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src, int n,
                                                 uint8_t* dst, int cap,
                                                 const uint8_t* __restrict__ dict, int dsz, int lane, uint32_t* bitmap,
-                                                uint8_t* ring)
+                                                uint8_t* ring, TeamShared* ts = nullptr)
 {
     constexpr int kBatchBytes = 1024;               // output bytes one batch may span (32 bitmap words)
     constexpr int kMaxBatchLit = 63;                // longest literal run a batched sequence may carry (6 bits)
@@ -147,6 +206,8 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
     if (n == 0) return -1;
 
     int ip = 0, op = 0;
+    int t_head = 0, t_g = 0;                        // kTeam: batches published, chunk index modulo the copy warps
+    int t_pf = 0;                                   // kTeam: the compressed stream has been asked into L1 up to here
     const bool check_offset = dsz < 65536;
     // word-aligned view of the compressed stream: byte q of src is byte (d4 + q) of src4
     const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
@@ -161,6 +222,16 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
         // offset [+ one length byte]); walking the token chain is then one shuffle per sequence instead of three
         // dependent loads.  Headers that do not fit the simple shape (literal nibble 15, more than one length
         // byte, too close to the end of the input) end the batch and go through decode_one.
+        if constexpr (kTeam) {
+            // the parse is a chain of dependent window loads: keep the stream 1-3 KiB ahead in L1 (the copy warps' literal
+            // loads follow the same lines)
+            if (ip + 1024 > t_pf) {
+                if (t_pf < ip) t_pf = ip & ~127;
+                const int at = t_pf + 128 * lane;
+                if (lane < 16 && at < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + at));
+                t_pf += 2048;
+            }
+        }
         int nseq = 0;
         int my_lit = 0, my_litpos = 0, my_mlen = 0;
         // input position after my sequence: literals, offset, and the one extension byte a match nibble of 15 carries
@@ -249,9 +320,28 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                 const uint32_t badmask = __ballot_sync(FULL_MASK, bad);
                 if (badmask) return -__shfl_sync(FULL_MASK, my_ipn(), __ffs(badmask) - 1) - 1;
 
-                // ---- 3. copy: 32 output bytes per step, one per lane
                 const int out0 = op;
                 const int out1 = __shfl_sync(FULL_MASK, o + span, nseq - 1);
+                if constexpr (kTeam) {
+                    // ---- 3'. publish the batch: the copy warps take it from here
+                    TeamSlot& sl = ts->slot[t_head % kTeamSlots];
+                    if (t_head >= kTeamSlots && !team_wait_passed(ts, t_head - kTeamSlots + 1, lane)) return PLZ4CU_E_STALL_;
+                    const int orel = mine ? o - out0 : 0;
+                    sl.bits[lane] = 0;
+                    __syncwarp();
+                    if (mine) atomicOr(&sl.bits[orel >> 5], 1u << (orel & 31));
+                    sl.packA[lane] = (uint32_t)(orel & 0x3FF) | ((uint32_t)my_lit << 10) | (my_off << 16);
+                    sl.litpos[lane] = my_litpos;
+                    if (lane == 0) { sl.nseq = nseq; sl.out0 = out0; sl.out1 = out1; sl.g0 = t_g; }
+                    __syncwarp();
+                    if (lane == 0) { __threadfence_block(); ts->head = t_head + 1; }
+                    t_head++;
+                    t_g = (t_g + ((out1 - out0 + 31) >> 5)) % kTeamCopyWarps;
+                    ip = __shfl_sync(FULL_MASK, my_ipn(), nseq - 1);
+                    op = out1;
+                    continue;
+                }
+                // ---- 3. copy: 32 output bytes per step, one per lane
                 const int orel = mine ? o - out0 : 0x7FFFFFF;                 // sequences outside the batch start "never"
                 // bitmap of sequence starts over the batch's output range: lane j ends up with bits out0+32j .. out0+32j+31
                 bitmap[lane] = 0;
@@ -304,6 +394,10 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
         // ---- anything that is not a shortcut sequence: one sequence through the literal state machine
         int32_t ret = 0;
         const int op_before = op;
+        if constexpr (kTeam) {
+            // decode_one reads earlier output from global memory: everything published must have been written
+            if (!team_wait_passed(ts, t_head, lane)) return PLZ4CU_E_STALL_;
+        }
         if (decode_one<kDict>(src, n, dst, cap, dict, dsz, lane, ip, op, ret) == kStepDone) return ret;
         __syncwarp();                                   // its stores may be the next batch's match sources
         if (kRing) {
@@ -366,19 +460,201 @@ lz4_decompress_kernel(DecodeArgs a)
     if (lane == 0) a.out_len[b] = r;
 }
 
+// ---------------------------------------------------------------- team decode: copy warps and kernel
+
+// Copy warp `w` of a team: takes every published batch in order and produces the chunks dealt to it.
+template <bool kDict>
+__device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restrict__ src, uint8_t* dst,
+                                          const uint8_t* __restrict__ dict, int dsz, uint8_t* ring, int w, int lane, int dbg)
+{
+    int known = 0;                                  // every output byte below this is known to be written
+    for (int k = 0;; k++) {
+        for (int spins = 0;; spins++) {
+            // lane 0 looks, everybody follows: quit is raised after the last batch is published, so it is read first
+            uint32_t see = 0;
+            if (lane == 0) {
+                const uint32_t q = (uint32_t)ts->quit, st = (uint32_t)ts->stall;
+                see = (uint32_t)ts->head | (q << 30) | (st << 31);
+            }
+            see = __shfl_sync(FULL_MASK, see, 0);
+            if ((int)(see & 0x3FFFFFFFu) > k) break;
+            if (see >> 30) return;                  // nothing more will come (or the watchdog fired)
+            if (spins > kTeamSpinLimit) {
+                if (lane == 0) ts->stall = 1;
+                return;
+            }
+        }
+        __threadfence_block();
+        const TeamSlot& sl = ts->slot[k % kTeamSlots];
+        const int nseq = sl.nseq, out0 = sl.out0, out1 = sl.out1, g0 = sl.g0;
+        const uint32_t packA = sl.packA[lane];
+        const int my_litpos = sl.litpos[lane];
+        const uint32_t my_bits = sl.bits[lane];
+        const int orel = lane < nseq ? (int)(packA & 0x3FFu) : 0x7FFFFFF;   // sequences outside the batch start "never"
+        const int len = out1 - out0;
+        const int nch = (len + 31) >> 5;
+        int j = w - g0;                             // my first chunk of this batch
+        if (j < 0) j += kTeamCopyWarps;
+        __syncwarp();
+        if (lane == 0) ts->prog[w] = j < nch ? out0 + 32 * j : out1;
+        if (dbg & 1) j = nch;                        // measurements: the parser alone
+        for (; j < nch; j += kTeamCopyWarps) {
+            const int c = 32 * j;
+            const int xr = c + lane;                                                        // byte position relative to out0
+            const uint32_t sbits = __shfl_sync(FULL_MASK, my_bits, j);
+            const int q = __popc(__ballot_sync(FULL_MASK, orel < c)) - 1 + __popc(sbits & ((2u << lane) - 1u));
+            const uint32_t ka = __shfl_sync(FULL_MASK, packA, q);
+            const int kp = __shfl_sync(FULL_MASK, my_litpos, q);
+            const bool live = xr < len;
+            const int d = xr - (int)(ka & 0x3FFu);                                          // byte index inside the sequence
+            const bool is_lit = d < (int)((ka >> 10) & 63u);
+            const int sr = xr - (int)(ka >> 16);                                            // match source, relative to out0
+            const bool fwd = live && !is_lit && sr >= c;                                    // source inside this chunk
+            const int s = out0 + sr;
+            uint32_t val = 0;
+            if (live && is_lit) val = src[kp + d];                                          // literals wait for nobody
+            // the match sources of this chunk that other chunks produce
+            const bool ext = live && !is_lit && !fwd && s >= 0;
+            const int need = __reduce_max_sync(FULL_MASK, ext ? s + 1 : 0);
+            if (need > known && !(dbg & 2)) {     // dbg 2: measurements, no waiting for sources
+                if (!team_wait_prog(ts, need, lane)) return;
+                known = need;
+            }
+            if (live && !is_lit && !fwd) {
+                if (kDict && s < 0) val = dict[dsz + s];
+                else val = (ka >> 16) > (uint32_t)kTeamFar ? dst[s] : ring[s & 0xFFFF];
+            }
+            if (__any_sync(FULL_MASK, fwd)) {
+                int root = fwd ? (sr - c) : lane;
+#pragma unroll
+                for (int it = 0; it < 5; it++) root = __shfl_sync(FULL_MASK, root, root);
+                val = __shfl_sync(FULL_MASK, val, root);
+            }
+            if (live) {
+                dst[out0 + xr] = (uint8_t)val;
+                ring[(out0 + xr) & 0xFFFF] = (uint8_t)val;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                ts->prog[w] = j + kTeamCopyWarps < nch ? out0 + 32 * (j + kTeamCopyWarps) : out1;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ts->passed[w] = k + 1;
+    }
+}
+
+template <bool kDict>
+__global__ void __launch_bounds__(kTeamThreads)
+lz4_decompress_team_kernel(DecodeArgs a, int dbg)
+{
+    extern __shared__ __align__(16) uint8_t dyn_smem[];              // 64 KiB output window, then the team's state
+    uint8_t* ring = dyn_smem;
+    TeamShared* ts = reinterpret_cast<TeamShared*>(dyn_smem + 65536);
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x;
+
+    if (threadIdx.x < kTeamCopyWarps) { ts->prog[threadIdx.x] = 0; ts->passed[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) { ts->head = 0; ts->quit = 0; ts->stall = 0; ts->hash_state = 0; }
+    __syncthreads();
+
+    const uint8_t* rec = a.rec_base + a.rec_off[b];
+    uint8_t* out = a.dst_base + (uint64_t)b * a.dst_stride;
+    const uint8_t* payload;
+    uint32_t csize;
+    bool stored = false;
+    bool verify = false;
+    if (a.raw_blocks) {
+        payload = rec;
+        csize = a.raw_len[b];
+    } else {
+        const uint32_t word = load_le32(rec);
+        stored = (word & 0x80000000u) != 0;
+        csize = word & 0x7FFFFFFFu;
+        payload = rec + 4;
+        if (csize > a.dst_cap) {                                      // blk/frame.go:79-81
+            if (threadIdx.x == 0) a.out_len[b] = PLZ4CU_E_OVERFLOW_;
+            return;
+        }
+        verify = a.verify_checksum != 0;
+    }
+
+    if (warp == kTeamCopyWarps + 1) {
+        // checksum warp (blk/frame.go:114-127): runs beside the decode, its verdict outranks the decoder's
+        if (verify) {
+            const uint32_t want = load_le32(payload + csize);
+            const uint32_t got = warp_xxh32(payload, csize, lane);
+            __syncwarp();
+            if (lane == 0) ts->hash_state = want == got ? 1 : 2;
+        }
+        if (!stored) return;
+    }
+
+    if (stored) {
+        // straight copy (async/reader.go:149-164), a slice per warp
+        if (warp <= kTeamCopyWarps) {
+            const uint32_t piece = ((csize + kTeamCopyWarps) / (kTeamCopyWarps + 1) + 511u) & ~511u;
+            const uint32_t lo = min(csize, (uint32_t)warp * piece), hi = min(csize, lo + piece);
+            if (hi > lo) warp_copy(out + lo, payload + lo, hi - lo, lane);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) a.out_len[b] = (verify && ts->hash_state == 2) ? PLZ4CU_E_BLOCKHASH_ : (int32_t)csize;
+        return;
+    }
+
+    if (warp == 0) {
+        int32_t r = decode_block<kDict, true, true>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane,
+                                                    ts->window, ring, ts);
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); ts->quit = 1; }
+        if (verify) {
+            int hs = 0;
+            for (int spins = 0; (hs = ts->hash_state) == 0; spins++) {
+                if (spins > kTeamSpinLimit) { hs = 3; break; }
+                __nanosleep(200);
+            }
+            if (hs == 2) r = PLZ4CU_E_BLOCKHASH_;
+            else if (hs == 3) r = PLZ4CU_E_STALL_;
+        }
+        if (ts->stall) r = PLZ4CU_E_STALL_;
+        if (lane == 0) a.out_len[b] = r;
+    } else {
+        team_copy<kDict>(ts, payload, out, a.dict, (int)a.dict_size, ring, warp - 1, lane, dbg);
+    }
+}
+
 constexpr uint32_t kRingBlocks = 1024;          // launches with fewer blocks than this use the ring kernel
 constexpr int kRingBytes = 65536;
+constexpr int kTeamSmem = 65536 + (int)sizeof(TeamShared);
+int g_team_dbg = 0;                             // PLZ4CU_TEAM_DBG: measurement switches of the team kernel (wrong output)
+int g_team = 1;                                 // PLZ4CU_TEAM=0: few large blocks go back to one warp per block (measurements);
+                                                // =2: every launch below kRingBlocks blocks takes the team kernel (tests)
 
 cudaError_t configure_decompress()
 {
     cudaError_t e = cudaFuncSetAttribute(lz4_decompress_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lz4_decompress_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
+    e = cudaFuncSetAttribute(lz4_decompress_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lz4_decompress_team_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem);
+    if (e != cudaSuccess) return e;
+    if (const char* v = getenv("PLZ4CU_TEAM")) g_team = atoi(v);
+    if (const char* v = getenv("PLZ4CU_TEAM_DBG")) g_team_dbg = atoi(v);
+    return cudaFuncSetAttribute(lz4_decompress_team_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem);
 }
 
 cudaError_t launch_decompress(const DecodeArgs& a, cudaStream_t stream)
 {
     if (a.nblk == 0) return cudaSuccess;
+    if (g_team && a.nblk < kRingBlocks && (a.dst_cap > 65536u || g_team == 2)) {
+        // few, large blocks: one CTA per block (parser warp, copy warps, checksum warp), up to 3 CTAs per SM
+        dim3 grid(a.nblk), block(kTeamThreads);
+        if (a.dict_size > 0) lz4_decompress_team_kernel<true><<<grid, block, kTeamSmem, stream>>>(a, g_team_dbg);
+        else lz4_decompress_team_kernel<false><<<grid, block, kTeamSmem, stream>>>(a, g_team_dbg);
+        return cudaGetLastError();
+    }
     if (a.nblk < kRingBlocks && a.dst_cap > 65536u) {
         // few, large blocks: one warp per CTA with a shared-memory window (up to 3 CTAs per SM)
         dim3 grid(a.nblk), block(32);

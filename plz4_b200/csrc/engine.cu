@@ -53,6 +53,7 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess)
 // host pipeline tunables (see "host-resident batches" below)
 constexpr int kMaxLanes = 8;
 int kLanes = 4;                                  // lanes in use                   (PLZ4CU_LANES)
+bool g_spin_wait = false;                        // busy-wait on the GPU instead of sleeping (PLZ4CU_SPIN, measurements)
 uint32_t kChunkBlocks = 2048;                    // blocks per chunk we aim for    (PLZ4CU_CHUNK_BLOCKS)
 const uint64_t kChunkMinBytes = 64ull << 20;     // ... but small payloads are gathered up to this many bytes
 const uint64_t kChunkBytes = 512ull << 20;       // upper bound on a chunk's input span
@@ -63,6 +64,7 @@ void read_tuning_env()
     std::call_once(once, [] {
         if (const char* e = getenv("PLZ4CU_LANES")) { int v = atoi(e); if (v >= 1 && v <= kMaxLanes) kLanes = v; }
         if (const char* e = getenv("PLZ4CU_CHUNK_BLOCKS")) { int v = atoi(e); if (v >= 1) kChunkBlocks = (uint32_t)v; }
+        if (const char* e = getenv("PLZ4CU_SPIN")) g_spin_wait = atoi(e) != 0;
     });
 }
 
@@ -119,7 +121,9 @@ struct HostBuf {
 // one pipeline lane: a stream plus its private scratch
 struct Lane {
     cudaStream_t st = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr;          // sizes of a compressed chunk are on the host
+    cudaEvent_t fin = nullptr;           // everything issued on the lane for its chunk has completed
+    bool fin_recorded = false;
     DevBuf in, out, packed, off, res, poff;
     HostBuf h_meta, h_res;      // pinned staging for small metadata (up / down)
 };
@@ -130,9 +134,13 @@ struct Pipe {
     int init()
     {
         if (ready) return 0;
+        // The host waits on events that block instead of spinning: a waiting call costs no core, which is what lets
+        // eight ranks (or many streams) share one host without starving each other's copy and hash threads.
+        const unsigned flags = cudaEventDisableTiming | (g_spin_wait ? 0u : (unsigned)cudaEventBlockingSync);
         for (auto& l : lane) {
             CU(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&l.done, flags));
+            CU(cudaEventCreateWithFlags(&l.fin, flags));
         }
         ready = true;
         return 0;
@@ -661,6 +669,7 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         g_launches += 3;
         CU(cudaMemcpyAsync(L.h_res.p, L.poff.p, (uint64_t)(cnt + 1) * 8, cudaMemcpyDeviceToHost, L.st));
         CU(cudaEventRecord(L.done, L.st));
+        L.fin_recorded = false;
         return 0;
     };
     // stage 2: once the sizes are known on the host, bring the packed records down
@@ -673,12 +682,16 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         const uint64_t total = hoff[cnt];
         if (out_pos + total > packed_cap) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: packed buffer too small");
         CU(cudaMemcpyAsync(hout + out_pos, L.packed.p, total, cudaMemcpyDeviceToHost, L.st));
+        CU(cudaEventRecord(L.fin, L.st));
+        L.fin_recorded = true;
         for (uint32_t i = 0; i <= cnt; i++) packed_off[c.b0 + i] = out_pos + hoff[i];
         out_pos += total;
         return 0;
     };
     auto finish = [&](int k) -> int {
-        CU(cudaStreamSynchronize(pp->lane[k % kLanes].st));
+        Lane& L = pp->lane[k % kLanes];
+        if (L.fin_recorded) CU(cudaEventSynchronize(L.fin));
+        else CU(cudaStreamSynchronize(L.st));             // error path: the chunk never got as far as post()
         return 0;
     };
     // chunk j is issued at step j, its packed bytes are requested at step j + kLanes - 1 (so kLanes - 1 younger
@@ -778,12 +791,13 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
             CU(cudaMemcpy2DAsync(hdst + (uint64_t)c.b0 * dst_stride, dst_stride, L.out.p, dstride, dst_cap, cnt,
                                  cudaMemcpyDeviceToHost, L.st));
         }
+        CU(cudaEventRecord(L.fin, L.st));
         return 0;
     };
     auto finish = [&](int k) -> int {
         Lane& L = pp->lane[k % kLanes];
         const Chunk& c = chunks[k];
-        CU(cudaStreamSynchronize(L.st));
+        CU(cudaEventSynchronize(L.fin));
         memcpy(out_len + c.b0, L.h_res.p, (size_t)(c.b1 - c.b0) * 4);
         return 0;
     };

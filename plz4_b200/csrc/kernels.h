@@ -7,6 +7,7 @@ namespace plz4 {
 
 constexpr int32_t PLZ4CU_E_BLOCKHASH_ = -0x7F000001;
 constexpr int32_t PLZ4CU_E_OVERFLOW_ = -0x7F000002;
+constexpr int32_t PLZ4CU_E_STALL_ = -0x7F000003;       // a decode team's watchdog fired (never expected)
 
 constexpr int kDecodeThreads = 128;    // 4 warps = 4 blocks per CTA
 
