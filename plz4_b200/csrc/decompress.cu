@@ -131,74 +131,16 @@ __device__ __noinline__ int decode_one(const uint8_t* __restrict__ src, int n, u
     return kStepMore;
 }
 
-// ---------------------------------------------------------------- team decode: shared state (one CTA per block)
-//
-// A launch with few, large blocks (plz4's default 4 MiB block: 64 blocks per 256 MiB) cannot be filled by one warp per
-// block, and a lone warp is bound by its own instruction latency.  The team kernel gives a block one CTA: warp 0 parses
-// (steps 1 and 2 below, unchanged, so accept/reject and return codes stay those of the one-warp decoder) and publishes
-// batches of up to 32 sequences into a ring of slots; kTeamCopyWarps warps produce the output, 32-byte chunk by chunk,
-// chunks dealt round-robin over the warps across batch boundaries.  A chunk waits only for the output bytes its own
-// matches read (`prog`: per warp, the output position below which all of that warp's chunks are complete), so chunks
-// whose sources lie further back than the chunks in flight proceed in parallel; literals never wait.  One more warp
-// checks the block checksum meanwhile.
-constexpr int kTeamCopyWarps = 7;
-constexpr int kTeamSlots = 8;                                   // batches published ahead of the slowest copy warp
-constexpr int kTeamThreads = (kTeamCopyWarps + 2) * 32;         // parser + copy warps + checksum warp
-constexpr int kTeamFar = 65536 - 16384;                         // matches reaching further back read global memory: the ring
-                                                                // slots behind them may already belong to chunks in flight
-                                                                // (kTeamSlots batches of <= 1 KiB)
-constexpr int kTeamSpinLimit = 1 << 25;                         // watchdog: a stalled team reports PLZ4CU_E_STALL, it never hangs
-
-struct TeamSlot {
-    uint32_t packA[32];            // per sequence: start relative to out0 (10 bits) | literals (6 bits) | offset (16 bits)
-    int litpos[32];                // per sequence: position of its first literal in the compressed block
-    uint32_t bits[32];             // bitmap of sequence starts over the batch's output range
-    int nseq, out0, out1, g0;      // g0: index of the batch's first chunk, modulo kTeamCopyWarps
-};
-
-struct TeamShared {
-    TeamSlot slot[kTeamSlots];
-    uint32_t window[32];                       // parser scratch (header lengths of the current window)
-    volatile int prog[kTeamCopyWarps];
-    volatile int passed[kTeamCopyWarps];       // batches a copy warp has left behind
-    volatile int head;                         // batches published
-    volatile int quit;                         // no batch will follow `head`
-    volatile int stall;                        // watchdog fired
-    volatile int hash_state;                   // 0 running, 1 checksum ok, 2 mismatch
-};
-
-// Spin until every copy warp's entry of `arr` has reached `need`.  The decision is a warp vote, so the warp stays converged.
-__device__ __forceinline__ bool team_wait(TeamShared* ts, const volatile int* arr, int need, int lane)
-{
-    for (int spins = 0;; spins++) {
-        const int v = lane < kTeamCopyWarps ? arr[lane] : 0x7FFFFFFF;
-        const int st = ts->stall;
-        if (__all_sync(FULL_MASK, v >= need)) break;
-        if (__any_sync(FULL_MASK, st != 0) || spins > kTeamSpinLimit) {
-            if (lane == 0) ts->stall = 1;
-            return false;
-        }
-    }
-    __threadfence_block();
-    return true;
-}
-// all copy warps have left batch `need - 1` behind
-__device__ __forceinline__ bool team_wait_passed(TeamShared* ts, int need, int lane) { return team_wait(ts, ts->passed, need, lane); }
-// every output byte below `need` has been written
-__device__ __forceinline__ bool team_wait_prog(TeamShared* ts, int need, int lane) { return team_wait(ts, ts->prog, need, lane); }
-
 // ---------------------------------------------------------------- batched decode
 
 // kRing: the last 64 KiB of output are mirrored in a shared-memory ring and match sources are read from there.
 // Used when a launch has too few blocks to hide global-memory latency with other warps (large block sizes):
 // the per-chunk round trip drops from an L2/HBM access to a shared-memory access.
-// kTeam: the caller is the parser warp of a team (see above): batches are published to the copy warps instead of being
-// copied here; decode_one still runs on this warp, after the copy warps have drained.
-template <bool kDict, bool kRing, bool kTeam = false>
+template <bool kDict, bool kRing>
 __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src, int n,
                                                 uint8_t* dst, int cap,
                                                 const uint8_t* __restrict__ dict, int dsz, int lane, uint32_t* bitmap,
-                                                uint8_t* ring, TeamShared* ts = nullptr)
+                                                uint8_t* ring)
 {
     constexpr int kBatchBytes = 1024;               // output bytes one batch may span (32 bitmap words)
     constexpr int kMaxBatchLit = 63;                // longest literal run a batched sequence may carry (6 bits)
@@ -206,8 +148,6 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
     if (n == 0) return -1;
 
     int ip = 0, op = 0;
-    int t_head = 0, t_g = 0;                        // kTeam: batches published, chunk index modulo the copy warps
-    int t_pf = 0;                                   // kTeam: the compressed stream has been asked into L1 up to here
     const bool check_offset = dsz < 65536;
     // word-aligned view of the compressed stream: byte q of src is byte (d4 + q) of src4
     const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
@@ -222,16 +162,6 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
         // offset [+ one length byte]); walking the token chain is then one shuffle per sequence instead of three
         // dependent loads.  Headers that do not fit the simple shape (literal nibble 15, more than one length
         // byte, too close to the end of the input) end the batch and go through decode_one.
-        if constexpr (kTeam) {
-            // the parse is a chain of dependent window loads: keep the stream 1-3 KiB ahead in L1 (the copy warps' literal
-            // loads follow the same lines)
-            if (ip + 1024 > t_pf) {
-                if (t_pf < ip) t_pf = ip & ~127;
-                const int at = t_pf + 128 * lane;
-                if (lane < 16 && at < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + at));
-                t_pf += 2048;
-            }
-        }
         int nseq = 0;
         int my_lit = 0, my_litpos = 0, my_mlen = 0;
         // input position after my sequence: literals, offset, and the one extension byte a match nibble of 15 carries
@@ -320,28 +250,9 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                 const uint32_t badmask = __ballot_sync(FULL_MASK, bad);
                 if (badmask) return -__shfl_sync(FULL_MASK, my_ipn(), __ffs(badmask) - 1) - 1;
 
+                // ---- 3. copy: 32 output bytes per step, one per lane
                 const int out0 = op;
                 const int out1 = __shfl_sync(FULL_MASK, o + span, nseq - 1);
-                if constexpr (kTeam) {
-                    // ---- 3'. publish the batch: the copy warps take it from here
-                    TeamSlot& sl = ts->slot[t_head % kTeamSlots];
-                    if (t_head >= kTeamSlots && !team_wait_passed(ts, t_head - kTeamSlots + 1, lane)) return PLZ4CU_E_STALL_;
-                    const int orel = mine ? o - out0 : 0;
-                    sl.bits[lane] = 0;
-                    __syncwarp();
-                    if (mine) atomicOr(&sl.bits[orel >> 5], 1u << (orel & 31));
-                    sl.packA[lane] = (uint32_t)(orel & 0x3FF) | ((uint32_t)my_lit << 10) | (my_off << 16);
-                    sl.litpos[lane] = my_litpos;
-                    if (lane == 0) { sl.nseq = nseq; sl.out0 = out0; sl.out1 = out1; sl.g0 = t_g; }
-                    __syncwarp();
-                    if (lane == 0) { __threadfence_block(); ts->head = t_head + 1; }
-                    t_head++;
-                    t_g = (t_g + ((out1 - out0 + 31) >> 5)) % kTeamCopyWarps;
-                    ip = __shfl_sync(FULL_MASK, my_ipn(), nseq - 1);
-                    op = out1;
-                    continue;
-                }
-                // ---- 3. copy: 32 output bytes per step, one per lane
                 const int orel = mine ? o - out0 : 0x7FFFFFF;                 // sequences outside the batch start "never"
                 // bitmap of sequence starts over the batch's output range: lane j ends up with bits out0+32j .. out0+32j+31
                 bitmap[lane] = 0;
@@ -394,10 +305,6 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
         // ---- anything that is not a shortcut sequence: one sequence through the literal state machine
         int32_t ret = 0;
         const int op_before = op;
-        if constexpr (kTeam) {
-            // decode_one reads earlier output from global memory: everything published must have been written
-            if (!team_wait_passed(ts, t_head, lane)) return PLZ4CU_E_STALL_;
-        }
         if (decode_one<kDict>(src, n, dst, cap, dict, dsz, lane, ip, op, ret) == kStepDone) return ret;
         __syncwarp();                                   // its stores may be the next batch's match sources
         if (kRing) {
@@ -460,9 +367,448 @@ lz4_decompress_kernel(DecodeArgs a)
     if (lane == 0) a.out_len[b] = r;
 }
 
-// ---------------------------------------------------------------- team decode: copy warps and kernel
+// ---------------------------------------------------------------- team decode: one CTA per block
+//
+// A launch with few, large blocks (plz4's default 4 MiB block: 64 blocks per 256 MiB) cannot be filled by one warp per
+// block, and a lone warp is bound by its own instruction latency: walking the token chain (one dependent shared-memory
+// load per sequence) is more than a third of it, header decode and the scan most of the rest.  The team kernel gives a
+// block one CTA and the work five roles, each a stage that only waits for the stage before it:
+//
+//  * TABLE warps look at every byte position of a superwindow (4 KiB of compressed bytes at a fixed place: 32 segments
+//    of 128, one per lane) as if a token started there: literal count, match length, whether it fits the batched shape,
+//    and where the chain that starts there leaves the segment — a backward pass per lane in which position q looks up
+//    position q + header(q), already done.  Nothing in it depends on where the true chain runs, so superwindows are
+//    prepared ahead of the parse, several at a time.
+//  * the PARSER follows the true chain: one lookup per segment, then every lane lists the tokens of its own segment;
+//    the list goes out in batches of 32 sequences with the output position of each batch.  Tokens that do not fit the
+//    batched shape, and everything near the end of the block, go through decode_one on this warp after the others have
+//    drained — so accept/reject and return codes are those of the one-warp decoder.
+//  * DECODER warps take batches round-robin: offsets, output positions by prefix sum, the checks that depend on them
+//    (the first failing sequence in stream order decides the block's code), the bitmap of sequence starts; they publish
+//    in order into a ring of slots.
+//  * COPY warps produce the bytes, 32-byte chunk by chunk, chunks dealt round-robin.  A chunk waits only for the output
+//    its own matches read (`prog`: per warp, the position below which all of that warp's chunks are complete), so
+//    chunks whose sources lie further back than the chunks in flight proceed in parallel; literals never wait.
+//  * one warp verifies the block checksum meanwhile.
+constexpr int kTeamTabs = 3;                                    // superwindow tables; table warp t owns table t and prepares
+constexpr int kTeamTabWarps = kTeamTabs;                        // superwindows t, t + 3, ...: two are ahead of the parser's
+constexpr int kTeamDecWarps = 3;
+constexpr int kTeamCopyWarps = 8;
+constexpr int kTeamWarps = 1 + kTeamTabWarps + kTeamDecWarps + kTeamCopyWarps + 1;
+constexpr int kTeamThreads = kTeamWarps * 32;
+constexpr int kTeamSeqRing = 64;                                // batches between parser and decoders
+constexpr int kTeamSlots = 16;                                  // batches between decoders and copy warps
+constexpr int kTeamWindow = 32768;                              // output bytes that may be in flight; matches reaching further
+                                                                // back than kTeamWindow - 1 read global memory, not the ring
+constexpr int kTeamSpinLimit = 1 << 25;                         // watchdog: a stalled team reports PLZ4CU_E_STALL, it never hangs
+constexpr int kSwBytes = 4096;                                  // superwindow
+constexpr int kSwSlack = 128;                                   // bytes past it a header may touch (<= 68)
+constexpr int kSwWords = (kSwBytes + kSwSlack) / 4;
+constexpr int kSwMaxBatch = (kSwBytes / 3 + 3 + 31) / 32;       // a sequence header is at least 3 bytes
+static_assert(kSwMaxBatch <= kTeamSeqRing, "a superwindow's batches must fit the ring");
+constexpr int kTeamCapMargin = 128;                             // batched sequences end at least this far below the capacity
 
-// Copy warp `w` of a team: takes every published batch in order and produces the chunks dealt to it.
+// per-position word of the backward pass
+constexpr uint32_t kExPosMask = 0x1FFFu;        // bits 0-12: where the chain from here leaves the segment (superwindow-relative)
+constexpr uint32_t kExStop = 0x2000u;           // bit 13: ... it does not: it stops at that position (a token decode_one must take)
+constexpr int kExLitShift = 14;                 // bits 14-19: literal count (<= 63)
+constexpr int kExMlenShift = 20;                // bits 20-28: match length (<= 273)
+constexpr uint32_t kExBad = 1u << 30;           // the token here does not fit the batched shape
+
+__device__ __forceinline__ int ex_lit(uint32_t wd) { return (int)((wd >> kExLitShift) & 63u); }
+__device__ __forceinline__ int ex_mlen(uint32_t wd) { return (int)((wd >> kExMlenShift) & 0x1FFu); }
+// header length: token, [literal extension], literals, offset, [match extension]
+__device__ __forceinline__ int ex_dl(int lit, int mlen) { return (lit >= 15 ? 2 : 1) + lit + 2 + (mlen >= MINMATCH + 15 ? 1 : 0); }
+
+struct TeamSeqBatch {                           // parser -> decoder
+    int nseq, out0, ip0, pad;
+    uint32_t rec[32];                           // token position relative to ip0 (13 bits) | literals << 13 | match length << 19
+};
+struct TeamSlot {                               // decoder -> copy warps
+    uint32_t packA[32];                         // per sequence: start relative to out0 (10 bits) | literals (6 bits) | offset (16 bits)
+    int litpos[32];                             // per sequence: position of its first literal in the compressed block
+    uint32_t bits[32];                          // bitmap of sequence starts over the slot's output range (<= 1024 bytes)
+    int nseq, out0, out1, pad;
+};
+
+struct TeamShared {
+    uint32_t tab[kTeamTabs][128 * 32];          // per-position words, [position in segment][segment]
+    uint32_t cw[kTeamTabWarps][kSwWords + kSwWords / 32 + 2];   // a table warp's superwindow bytes (one word of padding per
+                                                                // 32: lane l reads word j of its segment from bank l + j)
+    TeamSeqBatch sb[kTeamSeqRing];
+    TeamSlot slot[kTeamSlots];
+    unsigned long long err;                     // first failing sequence: (batch * 32 + lane) << 32 | code
+    volatile int tab_ready[kTeamTabs];          // the superwindow a table describes
+    volatile int parser_sw;                     // the superwindow the parser is in; tables of earlier ones are free
+    volatile int sb_head;                       // batches listed by the parser
+    volatile int dec_next[kTeamDecWarps];       // the batch a decoder will read next
+    volatile int dec_done;                      // batches the decoders have dealt with, in order
+    volatile int head;                          // slots published
+    volatile int pend;                          // output position the published slots end at
+    volatile int prog[kTeamCopyWarps];
+    volatile int passed[kTeamCopyWarps];        // slots a copy warp has left behind
+    volatile int quit;                          // nothing will be listed any more
+    volatile int stall;                         // watchdog fired
+    volatile int hash_state;                    // 0 running, 1 checksum ok, 2 mismatch
+};
+
+// Spin until the first `cnt` entries of `arr` have all reached `need`.  The decision is a warp vote: the warp stays converged.
+__device__ __forceinline__ bool team_wait(TeamShared* ts, const volatile int* arr, int cnt, int need, int lane)
+{
+    for (int spins = 0;; spins++) {
+        const int v = lane < cnt ? arr[lane] : 0x7FFFFFFF;
+        const int st = ts->stall;
+        if (__all_sync(FULL_MASK, v >= need)) break;
+        if (__any_sync(FULL_MASK, st != 0) || spins > kTeamSpinLimit) {
+            if (lane == 0) ts->stall = 1;
+            return false;
+        }
+    }
+    __threadfence_block();
+    return true;
+}
+
+// Lane 0 looks at a counter and at the quit / stall flags (flags first: quit is raised after the last publication),
+// everybody gets the same answer: the counter, or -1 once nothing more can come.
+__device__ __forceinline__ int team_poll(TeamShared* ts, const volatile int* counter, int want_above, int lane)
+{
+    int r = 0;
+    if (lane == 0) {
+        const int flags = (ts->quit ? 1 : 0) | (ts->stall ? 2 : 0);
+        const int c = *counter;
+        r = c > want_above ? c : (flags ? -1 : c);
+    }
+    return __shfl_sync(FULL_MASK, r, 0);
+}
+
+__device__ __forceinline__ int sw_skew(int word) { return word + (word >> 5); }
+
+// ---- a table warp: superwindows t, t + kTeamTabs, ... into table t
+__device__ __forceinline__ void team_tables(TeamShared* ts, const uint8_t* __restrict__ src, int n, int t, int lane)
+{
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+    const uint32_t* __restrict__ src4 = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+    const uint32_t d4 = (uint32_t)sa & 3u;
+    const uint32_t last4 = (d4 + (uint32_t)n - 1u) >> 2;         // last word holding a valid byte
+    uint32_t* const cw = ts->cw[t];
+    const int nsw = (n + kSwBytes - 1) / kSwBytes;
+
+    for (int k = t;; k += kTeamTabWarps) {
+        // skip what the parser has left behind; wait for a free table
+        for (int spins = 0;; spins++) {
+            int psw = 0;
+            if (lane == 0) psw = (ts->quit | ts->stall) ? -1 : ts->parser_sw;
+            psw = __shfl_sync(FULL_MASK, psw, 0);
+            if (psw < 0) return;
+            if (k < psw) k += (psw - k + kTeamTabWarps - 1) / kTeamTabWarps * kTeamTabWarps;
+            if (k >= nsw) return;
+            if (k < psw + kTeamTabs) break;
+            if (spins > kTeamSpinLimit) {
+                if (lane == 0) ts->stall = 1;
+                return;
+            }
+        }
+        __threadfence_block();
+        uint32_t* const ex = ts->tab[k % kTeamTabs];
+        const int sw_ip = k * kSwBytes;
+        // ---- bytes of the superwindow into shared memory (zero past the end of the block)
+        {
+            const uint32_t a0 = d4 + (uint32_t)sw_ip;
+            const uint32_t w0 = a0 >> 2, sh = (a0 & 3u) * 8u;
+            // word i of the window = aligned words w0+i and w0+i+1 funnel-shifted; rows of 32 words, the next row's first
+            // word comes along by shuffle
+            uint32_t row = (w0 + (uint32_t)lane) <= last4 ? src4[w0 + lane] : 0u;
+#pragma unroll 3
+            for (int r = 0; r < kSwWords / 32; r++) {
+                const uint32_t wi = w0 + (uint32_t)(32 * (r + 1) + lane);
+                const uint32_t nrow = wi <= last4 ? src4[wi] : 0u;               // the last one reads one row past the window
+                uint32_t hi = __shfl_down_sync(FULL_MASK, row, 1);
+                const uint32_t n0 = __shfl_sync(FULL_MASK, nrow, 0);
+                if (lane == 31) hi = n0;
+                cw[sw_skew(32 * r + lane)] = sh ? __funnelshift_r(row, hi, sh) : row;
+                row = nrow;
+            }
+            // ask for my next superwindow meanwhile
+            const int ahead = sw_ip + kTeamTabWarps * kSwBytes + 128 * lane;
+            if (ahead < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ahead));
+        }
+        __syncwarp();
+        // ---- backward pass: lane l owns segment l
+        const int seg0 = lane * 128;
+#pragma unroll 1
+        for (int j = 31; j >= 0; j--) {
+            const uint32_t w = cw[sw_skew(lane * 32 + j)];
+            const uint32_t wn = cw[sw_skew(lane * 32 + j + 1)];
+            // the four positions of this word: everything that depends on the bytes alone first ...
+            uint32_t lit4[4], ml4[4], dl4[4];
+            bool bad4[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t tok = (w >> (8 * i)) & 0xFFu;
+                const uint32_t nxt = (i < 3 ? (w >> (8 * i + 8)) : wn) & 0xFFu;
+                const int qs = seg0 + 4 * j + i;
+                const uint32_t L = tok >> 4, M = tok & 15u;
+                const bool longlit = L == 15u;
+                const uint32_t lit = longlit ? 15u + nxt : L;
+                const uint32_t hdr = (longlit ? 2u : 1u) + min(lit, 63u) + 2u;  // token .. offset
+                const int eb = qs + (int)hdr;                                    // where a match extension byte would be
+                const uint32_t ext = M == 15u ? (cw[sw_skew(eb >> 2)] >> ((eb & 3) * 8)) & 0xFFu : 0u;
+                const uint32_t dl = hdr + (M == 15u ? 1u : 0u);
+                const int pos = sw_ip + qs;
+                // the batched shape and its input-side limits (decode_block: `inwin`, `good`)
+                bad4[i] = lit > 63u || !(pos + 1 < n - 16) || (longlit && pos + 2 + (int)lit > n - 8) ||
+                          (M == 15u && (ext == 255u || pos + (int)dl > n - LASTLITERALS + 1));
+                lit4[i] = lit; ml4[i] = M + (uint32_t)MINMATCH + ext; dl4[i] = dl;
+            }
+            // ... then the chain lookups, last position first (a lookup may land on a position of this very word)
+#pragma unroll
+            for (int i = 3; i >= 0; i--) {
+                const int q = 4 * j + i;
+                const int t2 = q + (int)dl4[i];
+                uint32_t e;
+                if (bad4[i]) e = (uint32_t)(seg0 + q) | kExStop | kExBad;
+                else {
+                    if (t2 >= 128) e = (uint32_t)(seg0 + t2);
+                    else e = ex[t2 * 32 + lane] & (kExPosMask | kExStop);
+                    e |= (lit4[i] << kExLitShift) | (ml4[i] << kExMlenShift);
+                }
+                ex[q * 32 + lane] = e;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            ts->tab_ready[k % kTeamTabs] = k;
+        }
+    }
+}
+
+// ---- the parser warp
+template <bool kDict>
+__device__ __forceinline__ int32_t team_parse(const uint8_t* __restrict__ src, int n, uint8_t* dst, int cap,
+                                              const uint8_t* __restrict__ dict, int dsz, int lane, uint8_t* ring, TeamShared* ts)
+{
+    if (cap == 0) return (n == 1 && src[0] == 0) ? 0 : -1;
+    if (n == 0) return -1;
+
+    int ip = 0, op = 0;
+    int ks = -1;                    // superwindow whose table `ex` points at
+    const uint32_t* ex = nullptr;
+    int batches = 0;                // batches listed
+    bool tail = false;              // the output is within kTeamCapMargin of the capacity: decode_one to the end
+
+    for (;;) {
+        if (!tail) {
+            if ((ip >> 12) != ks) {
+                ks = ip >> 12;
+                if (lane == 0) ts->parser_sw = ks;
+                const volatile int* ready = &ts->tab_ready[ks % kTeamTabs];
+                for (int spins = 0;; spins++) {
+                    const int v = *ready;
+                    const int st = ts->stall;
+                    if (__all_sync(FULL_MASK, v == ks)) break;
+                    if (__any_sync(FULL_MASK, st != 0) || spins > kTeamSpinLimit) {
+                        if (lane == 0) ts->stall = 1;
+                        return PLZ4CU_E_STALL_;
+                    }
+                }
+                __threadfence_block();
+                ex = ts->tab[ks % kTeamTabs];
+            }
+            const int sw_ip = ks << 12;
+
+            // ---- the true chain: one lookup per segment from the entry position
+            int cur = ip - sw_ip;
+            int my_entry = -1;
+            bool stopped = false;
+            while (cur < kSwBytes) {
+                const int s = cur >> 7;
+                if (lane == s) my_entry = cur;
+                const uint32_t wd = ex[(cur & 127) * 32 + s];
+                cur = (int)(wd & kExPosMask);
+                if (wd & kExStop) { stopped = true; break; }
+            }
+            // `cur`: where this stretch ends (the stopping token, or the first token past the superwindow)
+            // ---- every lane measures its own segment: sequences and output bytes
+            int cnt = 0, sp = 0;
+            if (my_entry >= 0) {
+                const int end = stopped ? min(cur, (lane + 1) * 128) : (lane + 1) * 128;
+                for (int q = my_entry; q < end;) {
+                    const uint32_t wd = ex[(q & 127) * 32 + lane];
+                    const int lit = ex_lit(wd), mlen = ex_mlen(wd);
+                    cnt++;
+                    sp += lit + mlen;
+                    q += ex_dl(lit, mlen);
+                }
+            }
+            int icnt = cnt, isp = sp;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int uc = __shfl_up_sync(FULL_MASK, icnt, d), us = __shfl_up_sync(FULL_MASK, isp, d);
+                if (lane >= d) { icnt += uc; isp += us; }
+            }
+            const int ecnt = icnt - cnt, esp = isp - sp;           // exclusive
+            int total = __shfl_sync(FULL_MASK, icnt, 31);
+            int total_sp = __shfl_sync(FULL_MASK, isp, 31);
+            int next_ip = sw_ip + cur;
+            // near the capacity liblz4's end-of-block rules apply: stop the stretch before the first segment that gets there
+            const uint32_t over = __ballot_sync(FULL_MASK, my_entry >= 0 && op + isp > cap - kTeamCapMargin);
+            if (over) {
+                const int lc = __ffs(over) - 1;
+                total = __shfl_sync(FULL_MASK, ecnt, lc);
+                total_sp = __shfl_sync(FULL_MASK, esp, lc);
+                next_ip = sw_ip + __shfl_sync(FULL_MASK, my_entry, lc);
+                if (lane >= lc) cnt = 0;
+                tail = true;
+                stopped = true;
+            }
+            if (total > 0) {
+                // ---- list the stretch: batches of 32 sequences for the decoders
+                const int nb = (total + 31) >> 5;
+                if (!team_wait(ts, ts->dec_next, kTeamDecWarps, batches + nb - kTeamSeqRing, lane)) return PLZ4CU_E_STALL_;
+                if (cnt > 0) {
+                    int g = ecnt, o = op + esp;
+                    for (int q = my_entry, i = 0; i < cnt; i++, g++) {
+                        const uint32_t wd = ex[(q & 127) * 32 + lane];
+                        const int lit = ex_lit(wd), mlen = ex_mlen(wd);
+                        TeamSeqBatch& e = ts->sb[(batches + (g >> 5)) % kTeamSeqRing];
+                        e.rec[g & 31] = (uint32_t)q | ((uint32_t)lit << 13) | ((uint32_t)mlen << 19);
+                        if ((g & 31) == 0) e.out0 = o;
+                        o += lit + mlen;
+                        q += ex_dl(lit, mlen);
+                    }
+                }
+                for (int j = lane; j < nb; j += 32) {
+                    TeamSeqBatch& e = ts->sb[(batches + j) % kTeamSeqRing];
+                    e.nseq = min(32, total - 32 * j);
+                    e.ip0 = sw_ip;
+                }
+                batches += nb;
+                op += total_sp;
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    ts->sb_head = batches;
+                }
+            }
+            ip = next_ip;
+            if (!stopped) continue;                                 // the chain ran off the superwindow: next one
+        }
+
+        // ---- one sequence through the literal state machine, once everything listed has been written
+        if (!team_wait(ts, &ts->dec_done, 1, batches, lane)) return PLZ4CU_E_STALL_;
+        if (!team_wait(ts, ts->passed, kTeamCopyWarps, ts->head, lane)) return PLZ4CU_E_STALL_;
+        {
+            const unsigned long long err = ts->err;
+            if (err != ~0ull) return (int32_t)(uint32_t)err;
+        }
+        int32_t ret = 0;
+        const int op_before = op;
+        if (decode_one<kDict>(src, n, dst, cap, dict, dsz, lane, ip, op, ret) == kStepDone) return ret;
+        __syncwarp();
+        // decode_one works on global memory: mirror what it produced into the ring
+        for (int k = max(op_before, op - 65536) + lane; k < op; k += 32) ring[k & 0xFFFF] = dst[k];
+        __syncwarp();
+    }
+}
+
+// ---- a decoder warp: batches d, d + kTeamDecWarps, ...
+__device__ __forceinline__ void team_decode(TeamShared* ts, const uint8_t* __restrict__ src, int cap, int dsz, int d, int lane)
+{
+    const bool check_offset = dsz < 65536;
+    for (int b = d;; b += kTeamDecWarps) {
+        for (int spins = 0;; spins++) {
+            const int c = team_poll(ts, &ts->sb_head, b, lane);
+            if (c > b) break;
+            if (c < 0) return;
+            if (spins > kTeamSpinLimit) {
+                if (lane == 0) ts->stall = 1;
+                return;
+            }
+        }
+        __threadfence_block();
+        const TeamSeqBatch& e = ts->sb[b % kTeamSeqRing];
+        const int nseq = e.nseq, out0 = e.out0, ip0 = e.ip0;
+        const uint32_t rec = e.rec[lane];
+        const bool have = lane < nseq;
+        // ---- my sequence's header (decode_block step 1, from what the tables hold)
+        const int my_lit = have ? (int)((rec >> 13) & 63u) : 0;
+        const int my_mlen = have ? (int)(rec >> 19) : 0;
+        const int my_litpos = ip0 + (int)(rec & 0x1FFFu) + (my_lit >= 15 ? 2 : 1);
+        const int ob = my_litpos + my_lit;
+        const uint32_t my_off = have ? load_u16le(src + ob) : 0u;
+        const int my_ipn = ob + 2 + (my_mlen >= MINMATCH + 15 ? 1 : 0);
+        const bool my_simple = my_lit < 15 && my_mlen < MINMATCH + 15 && my_off >= 8u;
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            ts->dec_next[d] = b + kTeamDecWarps;                // the parser may reuse the entry
+        }
+        // ---- output positions and the checks that depend on them (decode_block step 2)
+        const int span = my_lit + my_mlen;
+        int incl = span;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int up = __shfl_up_sync(FULL_MASK, incl, s);
+            if (lane >= s) incl += up;
+        }
+        const int o = out0 + incl - span;
+        const int m = o + my_lit;
+        const int out1 = __shfl_sync(FULL_MASK, out0 + incl, 31);
+        const bool stage2 = my_simple && (int)my_off <= m;
+        const bool bad = have && !stage2 &&
+                         ((check_offset && m - (int)my_off + dsz < 0) || my_off == 0 || m + my_mlen > cap - LASTLITERALS);
+        const uint32_t badmask = __ballot_sync(FULL_MASK, bad);
+
+        // ---- my turn to publish
+        if (!team_wait(ts, &ts->dec_done, 1, b, lane)) return;
+        if (badmask) {
+            // the first failing sequence in stream order decides the block's code; nothing of this batch is written
+            const int f = __ffs(badmask) - 1;
+            const int code = -__shfl_sync(FULL_MASK, my_ipn, f) - 1;
+            if (lane == 0) atomicMin(&ts->err, ((unsigned long long)(uint32_t)(b * 32 + f) << 32) | (uint32_t)code);
+        } else {
+            // the ring holds 64 KiB: nothing may be published more than kTeamWindow ahead of the oldest unfinished byte
+            // (everything between the last slot and this batch is decode_one's, hence finished)
+            const int pend = ts->pend;
+            if (!team_wait(ts, ts->prog, kTeamCopyWarps, min(out1 - kTeamWindow, pend), lane)) return;
+            // slots of at most 1024 output bytes (the start bitmap's reach)
+            for (int first = 0; first < nseq;) {
+                const int base = __shfl_sync(FULL_MASK, o, first);
+                const uint32_t fits = __ballot_sync(FULL_MASK, lane >= first && have && o + span - base <= 1024);
+                const int cnt = __popc(fits);
+                const bool mine = lane >= first && lane < first + cnt;
+                const int end = __shfl_sync(FULL_MASK, o + span, first + cnt - 1);
+                const int h = ts->head;
+                if (!team_wait(ts, ts->passed, kTeamCopyWarps, h - kTeamSlots + 1, lane)) return;
+                TeamSlot& sl = ts->slot[h % kTeamSlots];
+                const int orel = o - base;
+                sl.bits[lane] = 0;
+                __syncwarp();
+                if (mine) {
+                    atomicOr(&sl.bits[orel >> 5], 1u << (orel & 31));
+                    sl.packA[lane - first] = (uint32_t)(orel & 0x3FF) | ((uint32_t)my_lit << 10) | (my_off << 16);
+                    sl.litpos[lane - first] = my_litpos;
+                }
+                if (lane == 0) { sl.nseq = cnt; sl.out0 = base; sl.out1 = end; }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    ts->pend = end;
+                    ts->head = h + 1;
+                }
+                first += cnt;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            ts->dec_done = b + 1;
+        }
+    }
+}
+
+// ---- a copy warp: takes every published slot in order and produces the chunks dealt to it
 template <bool kDict>
 __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restrict__ src, uint8_t* dst,
                                           const uint8_t* __restrict__ dict, int dsz, uint8_t* ring, int w, int lane, int dbg)
@@ -470,15 +816,12 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
     int known = 0;                                  // every output byte below this is known to be written
     for (int k = 0;; k++) {
         for (int spins = 0;; spins++) {
-            // lane 0 looks, everybody follows: quit is raised after the last batch is published, so it is read first
-            uint32_t see = 0;
-            if (lane == 0) {
-                const uint32_t q = (uint32_t)ts->quit, st = (uint32_t)ts->stall;
-                see = (uint32_t)ts->head | (q << 30) | (st << 31);
+            const int c = team_poll(ts, &ts->head, k, lane);
+            if (c > k) break;
+            if (c < 0) {
+                if (lane == 0) ts->prog[w] = 0x7FFFFFFF;
+                return;
             }
-            see = __shfl_sync(FULL_MASK, see, 0);
-            if ((int)(see & 0x3FFFFFFFu) > k) break;
-            if (see >> 30) return;                  // nothing more will come (or the watchdog fired)
             if (spins > kTeamSpinLimit) {
                 if (lane == 0) ts->stall = 1;
                 return;
@@ -486,18 +829,19 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
         }
         __threadfence_block();
         const TeamSlot& sl = ts->slot[k % kTeamSlots];
-        const int nseq = sl.nseq, out0 = sl.out0, out1 = sl.out1, g0 = sl.g0;
+        const int nseq = sl.nseq, out0 = sl.out0, out1 = sl.out1;
         const uint32_t packA = sl.packA[lane];
         const int my_litpos = sl.litpos[lane];
         const uint32_t my_bits = sl.bits[lane];
-        const int orel = lane < nseq ? (int)(packA & 0x3FFu) : 0x7FFFFFF;   // sequences outside the batch start "never"
+        const int orel = lane < nseq ? (int)(packA & 0x3FFu) : 0x7FFFFFF;   // sequences outside the slot start "never"
         const int len = out1 - out0;
         const int nch = (len + 31) >> 5;
-        int j = w - g0;                             // my first chunk of this batch
+        // chunks are dealt by where they lie in the output, so consecutive chunks go to different warps across slots too
+        int j = (w - (out0 >> 5)) % kTeamCopyWarps;
         if (j < 0) j += kTeamCopyWarps;
         __syncwarp();
         if (lane == 0) ts->prog[w] = j < nch ? out0 + 32 * j : out1;
-        if (dbg & 1) j = nch;                        // measurements: the parser alone
+        if (dbg & 1) j = nch;                        // measurements: everything but the copy
         for (; j < nch; j += kTeamCopyWarps) {
             const int c = 32 * j;
             const int xr = c + lane;                                                        // byte position relative to out0
@@ -514,15 +858,15 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
             uint32_t val = 0;
             if (live && is_lit) val = src[kp + d];                                          // literals wait for nobody
             // the match sources of this chunk that other chunks produce
-            const bool ext = live && !is_lit && !fwd && s >= 0;
-            const int need = __reduce_max_sync(FULL_MASK, ext ? s + 1 : 0);
-            if (need > known && !(dbg & 2)) {     // dbg 2: measurements, no waiting for sources
-                if (!team_wait_prog(ts, need, lane)) return;
+            const bool extn = live && !is_lit && !fwd && s >= 0;
+            const int need = __reduce_max_sync(FULL_MASK, extn ? s + 1 : 0);
+            if (need > known && !(dbg & 2)) {
+                if (!team_wait(ts, ts->prog, kTeamCopyWarps, need, lane)) return;
                 known = need;
             }
             if (live && !is_lit && !fwd) {
                 if (kDict && s < 0) val = dict[dsz + s];
-                else val = (ka >> 16) > (uint32_t)kTeamFar ? dst[s] : ring[s & 0xFFFF];
+                else val = (ka >> 16) >= (uint32_t)kTeamWindow ? dst[s] : ring[s & 0xFFFF];
             }
             if (__any_sync(FULL_MASK, fwd)) {
                 int root = fwd ? (sr - c) : lane;
@@ -541,7 +885,10 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
             }
         }
         __syncwarp();
-        if (lane == 0) ts->passed[w] = k + 1;
+        if (lane == 0) {
+            __threadfence_block();
+            ts->passed[w] = k + 1;
+        }
     }
 }
 
@@ -557,7 +904,12 @@ lz4_decompress_team_kernel(DecodeArgs a, int dbg)
     const uint32_t b = blockIdx.x;
 
     if (threadIdx.x < kTeamCopyWarps) { ts->prog[threadIdx.x] = 0; ts->passed[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) { ts->head = 0; ts->quit = 0; ts->stall = 0; ts->hash_state = 0; }
+    if (threadIdx.x < kTeamDecWarps) ts->dec_next[threadIdx.x] = threadIdx.x;
+    if (threadIdx.x < kTeamTabs) ts->tab_ready[threadIdx.x] = -1;
+    if (threadIdx.x == 0) {
+        ts->err = ~0ull; ts->parser_sw = 0; ts->sb_head = 0; ts->dec_done = 0; ts->head = 0; ts->pend = 0;
+        ts->quit = 0; ts->stall = 0; ts->hash_state = 0;
+    }
     __syncthreads();
 
     const uint8_t* rec = a.rec_base + a.rec_off[b];
@@ -581,7 +933,7 @@ lz4_decompress_team_kernel(DecodeArgs a, int dbg)
         verify = a.verify_checksum != 0;
     }
 
-    if (warp == kTeamCopyWarps + 1) {
+    if (warp == kTeamWarps - 1) {
         // checksum warp (blk/frame.go:114-127): runs beside the decode, its verdict outranks the decoder's
         if (verify) {
             const uint32_t want = load_le32(payload + csize);
@@ -594,8 +946,8 @@ lz4_decompress_team_kernel(DecodeArgs a, int dbg)
 
     if (stored) {
         // straight copy (async/reader.go:149-164), a slice per warp
-        if (warp <= kTeamCopyWarps) {
-            const uint32_t piece = ((csize + kTeamCopyWarps) / (kTeamCopyWarps + 1) + 511u) & ~511u;
+        if (warp < kTeamWarps - 1) {
+            const uint32_t piece = ((csize + kTeamWarps - 2) / (kTeamWarps - 1) + 511u) & ~511u;
             const uint32_t lo = min(csize, (uint32_t)warp * piece), hi = min(csize, lo + piece);
             if (hi > lo) warp_copy(out + lo, payload + lo, hi - lo, lane);
         }
@@ -605,8 +957,7 @@ lz4_decompress_team_kernel(DecodeArgs a, int dbg)
     }
 
     if (warp == 0) {
-        int32_t r = decode_block<kDict, true, true>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane,
-                                                    ts->window, ring, ts);
+        int32_t r = team_parse<kDict>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane, ring, ts);
         __syncwarp();
         if (lane == 0) { __threadfence_block(); ts->quit = 1; }
         if (verify) {
@@ -620,8 +971,12 @@ lz4_decompress_team_kernel(DecodeArgs a, int dbg)
         }
         if (ts->stall) r = PLZ4CU_E_STALL_;
         if (lane == 0) a.out_len[b] = r;
+    } else if (warp <= kTeamTabWarps) {
+        if (csize > 0 && a.dst_cap > 0) team_tables(ts, payload, (int)csize, warp - 1, lane);
+    } else if (warp <= kTeamTabWarps + kTeamDecWarps) {
+        team_decode(ts, payload, (int)a.dst_cap, (int)a.dict_size, warp - 1 - kTeamTabWarps, lane);
     } else {
-        team_copy<kDict>(ts, payload, out, a.dict, (int)a.dict_size, ring, warp - 1, lane, dbg);
+        team_copy<kDict>(ts, payload, out, a.dict, (int)a.dict_size, ring, warp - 1 - kTeamTabWarps - kTeamDecWarps, lane, dbg);
     }
 }
 
