@@ -23,6 +23,8 @@
  *                      -(byte offset)-1        the LZ4_decompress_safe code (clz4.go:47-60, lz4.c:2443)
  *                      PLZ4CU_E_BLOCKHASH      xxh32 mismatch          (blk/frame.go:114-127)
  *                      PLZ4CU_E_OVERFLOW       size word > block size  (blk/frame.go:79-81)
+ *                      PLZ4CU_E_STALL          engine fault (a decode team's watchdog fired): map it like a
+ *                                              PLZ4CU_ERR_* failure, not like corrupted data
  */
 #ifndef PLZ4CU_H
 #define PLZ4CU_H

@@ -18,6 +18,7 @@ HEADER = os.path.join(_HERE, "..", "include", "plz4cu.h")
 ERR_CUDA, ERR_ARG, ERR_NOMEM, ERR_NODEVICE = -1, -2, -3, -4
 E_BLOCKHASH = -0x7F000001
 E_OVERFLOW = -0x7F000002
+E_STALL = -0x7F000003
 STORED_BIT = 0x80000000
 INT32_MIN = -(1 << 31)
 

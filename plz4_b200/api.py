@@ -16,7 +16,7 @@ from typing import Iterable, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import E_BLOCKHASH, E_OVERFLOW, INT32_MIN, STORED_BIT, Plz4cuError, check
+from ._lib import E_BLOCKHASH, E_OVERFLOW, E_STALL, INT32_MIN, STORED_BIT, Plz4cuError, check
 
 BLOCK_IDX_64KB, BLOCK_IDX_256KB, BLOCK_IDX_1MB, BLOCK_IDX_4MB = 4, 5, 6, 7      # descriptor/index.go:5-14
 BLOCK_SIZES = {4: 64 << 10, 5: 256 << 10, 6: 1 << 20, 7: 4 << 20}
@@ -55,6 +55,8 @@ def block_error(code: int) -> Lz4Error:
         return Lz4Error(f"{ERR_CORRUPTED}: {ERR_BLOCK_HASH}", (ERR_CORRUPTED, ERR_BLOCK_HASH))
     if code == E_OVERFLOW:       # blk/frame.go:79-81
         return Lz4Error(f"{ERR_CORRUPTED}: {ERR_BLOCK_SIZE_OVERFLOW}", (ERR_CORRUPTED, ERR_BLOCK_SIZE_OVERFLOW))
+    if code == E_STALL:          # an engine fault, not a verdict on the data
+        raise Plz4cuError("a decode team stalled (PLZ4CU_E_STALL)")
     # compress/decompress.go:33-36 + clz4.go:55-57
     return Lz4Error(f"{ERR_CORRUPTED}\n{ERR_DECOMPRESS}\nlz4 fail decompress: code {code}", (ERR_CORRUPTED, ERR_DECOMPRESS))
 

@@ -43,12 +43,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *srcs]
+    tmp = LIB + f".{os.getpid()}.tmp"              # written beside the target, renamed when complete
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+    try:
+        subprocess.run(cmd, check=True)
+        os.replace(tmp, LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return LIB
 
 

@@ -23,6 +23,7 @@ using namespace plz4;
 
 static_assert(PLZ4CU_E_BLOCKHASH == PLZ4CU_E_BLOCKHASH_, "header/kernels mismatch");
 static_assert(PLZ4CU_E_OVERFLOW == PLZ4CU_E_OVERFLOW_, "header/kernels mismatch");
+static_assert(PLZ4CU_E_STALL == PLZ4CU_E_STALL_, "header/kernels mismatch");
 
 namespace {
 
@@ -526,6 +527,7 @@ int plz4cu_decompress_frame_device(plz4cu_stream_t stream, const void* frame, ui
         if (r < 0) {
             if (r == PLZ4CU_E_BLOCKHASH) return PLZ4CU_Z_BLOCK_HASH;
             if (r == PLZ4CU_E_OVERFLOW) return PLZ4CU_Z_BLOCK_SIZE_OVERFLOW;
+            if (r == PLZ4CU_E_STALL) return fail(PLZ4CU_Z_ENGINE, "decompress_frame_device: a decode team stalled");
             return PLZ4CU_Z_DECOMPRESS;
         }
         info->out_bytes += (uint64_t)r;

@@ -938,6 +938,7 @@ struct plz4cu_reader {
                 cur = b.nblk;                           // nothing after a bad block is served (the error is sticky)
                 if (r == PLZ4CU_E_BLOCKHASH) return PLZ4CU_Z_BLOCK_HASH;
                 if (r == PLZ4CU_E_OVERFLOW) return PLZ4CU_Z_BLOCK_SIZE_OVERFLOW;
+                if (r == PLZ4CU_E_STALL) return PLZ4CU_Z_ENGINE;    // an engine fault, not a verdict on the data
                 return PLZ4CU_Z_DECOMPRESS;
             }
             cur_off = 0; cur_len = (size_t)r;

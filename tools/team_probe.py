@@ -9,11 +9,13 @@ from plz4_b200._lib import check
 L = _lib.lib(); check(L.plz4cu_init(0))
 dev = torch.device("cuda", 0)
 p = lambda t: C.c_void_p(t.data_ptr())
-print("PLZ4CU_TEAM =", os.environ.get("PLZ4CU_TEAM", "(default)"), " PLZ4CU_TEAM_DBG =", os.environ.get("PLZ4CU_TEAM_DBG", "-"))
-for total in (256 << 20, 1 << 30):
+print("PLZ4CU_TEAM =", os.environ.get("PLZ4CU_TEAM", "(default)"), " PLZ4CU_TEAM_DBG =", os.environ.get("PLZ4CU_TEAM_DBG", "-"),
+      " PLZ4CU_TEAM_COPY =", os.environ.get("PLZ4CU_TEAM_COPY", "-"))
+QUICK = bool(os.environ.get("TEAM_PROBE_QUICK"))
+for total in ((256 << 20,) if QUICK else (256 << 20, 1 << 30)):
     src = torch.empty(total, dtype=torch.uint8, device=dev)
     check(L.plz4cu_gen_logtext_device(None, 0x504C5A34, 0, p(src), total))
-    for bsz in (262144, 1 << 20, 4 << 20):
+    for bsz in ((4 << 20,) if QUICK else (262144, 1 << 20, 4 << 20)):
         nblk = total // bsz; stride = bsz + 16
         if nblk >= 1024:
             continue
