@@ -1,4 +1,5 @@
-// decompress.cu — LZ4 block decode, one warp per block (sm_100a).
+// decompress.cu — LZ4 block decode (sm_100a): one warp per block when a launch has many blocks, one CTA per block
+// ("team", second half of this file) when it has few, large ones.
 //
 // Replaces, for a whole batch of independent blocks, what plz4 does per block on a goroutine:
 //   blk/frame.go:79-81      size word > block size            -> PLZ4CU_E_OVERFLOW
@@ -393,13 +394,14 @@ lz4_decompress_kernel(DecodeArgs a)
 constexpr int kTeamTabs = 3;                                    // superwindow tables; table warp t owns table t and prepares
 constexpr int kTeamTabWarps = kTeamTabs;                        // superwindows t, t + 3, ...: two are ahead of the parser's
 constexpr int kTeamDecWarps = 3;
-constexpr int kTeamCopyWarps = 8;
-constexpr int kTeamWarps = 1 + kTeamTabWarps + kTeamDecWarps + kTeamCopyWarps + 1;
-constexpr int kTeamThreads = kTeamWarps * 32;
+constexpr int kTeamCopyWarps = 16;                              // at most; a launch chooses how many (PLZ4CU_TEAM_COPY)
+constexpr int kTeamFirstCopy = 1 + kTeamTabWarps + kTeamDecWarps + 1;   // warps: parser, tables, decoders, checksum, copy...
+constexpr int kTeamThreads = (kTeamFirstCopy + kTeamCopyWarps) * 32;
 constexpr int kTeamSeqRing = 64;                                // batches between parser and decoders
 constexpr int kTeamSlots = 16;                                  // batches between decoders and copy warps
-constexpr int kTeamWindow = 32768;                              // output bytes that may be in flight; matches reaching further
-                                                                // back than kTeamWindow - 1 read global memory, not the ring
+// The output window in shared memory is a ring of R bytes (64 KiB with one team per SM, 32 KiB when two teams share an SM).
+// At most R/2 output bytes may be in flight, and matches reaching back R/2 or more read global memory instead of the
+// ring: then no chunk in flight can overwrite a ring byte another chunk in flight still reads.
 constexpr int kTeamSpinLimit = 1 << 25;                         // watchdog: a stalled team reports PLZ4CU_E_STALL, it never hangs
 constexpr int kSwBytes = 4096;                                  // superwindow
 constexpr int kSwSlack = 128;                                   // bytes past it a header may touch (<= 68)
@@ -450,6 +452,7 @@ struct TeamShared {
     volatile int quit;                          // nothing will be listed any more
     volatile int stall;                         // watchdog fired
     volatile int hash_state;                    // 0 running, 1 checksum ok, 2 mismatch
+    int ring_mask;                              // R - 1
 };
 
 // Spin until the first `cnt` entries of `arr` have all reached `need`.  The decision is a warp vote: the warp stays converged.
@@ -586,7 +589,8 @@ __device__ __forceinline__ void team_tables(TeamShared* ts, const uint8_t* __res
 // ---- the parser warp
 template <bool kDict>
 __device__ __forceinline__ int32_t team_parse(const uint8_t* __restrict__ src, int n, uint8_t* dst, int cap,
-                                              const uint8_t* __restrict__ dict, int dsz, int lane, uint8_t* ring, TeamShared* ts)
+                                              const uint8_t* __restrict__ dict, int dsz, int lane, uint8_t* ring, TeamShared* ts,
+                                              int nw)
 {
     if (cap == 0) return (n == 1 && src[0] == 0) ? 0 : -1;
     if (n == 0) return -1;
@@ -697,7 +701,7 @@ __device__ __forceinline__ int32_t team_parse(const uint8_t* __restrict__ src, i
 
         // ---- one sequence through the literal state machine, once everything listed has been written
         if (!team_wait(ts, &ts->dec_done, 1, batches, lane)) return PLZ4CU_E_STALL_;
-        if (!team_wait(ts, ts->passed, kTeamCopyWarps, ts->head, lane)) return PLZ4CU_E_STALL_;
+        if (!team_wait(ts, ts->passed, nw, ts->head, lane)) return PLZ4CU_E_STALL_;
         {
             const unsigned long long err = ts->err;
             if (err != ~0ull) return (int32_t)(uint32_t)err;
@@ -707,15 +711,18 @@ __device__ __forceinline__ int32_t team_parse(const uint8_t* __restrict__ src, i
         if (decode_one<kDict>(src, n, dst, cap, dict, dsz, lane, ip, op, ret) == kStepDone) return ret;
         __syncwarp();
         // decode_one works on global memory: mirror what it produced into the ring
-        for (int k = max(op_before, op - 65536) + lane; k < op; k += 32) ring[k & 0xFFFF] = dst[k];
+        const int rmask = ts->ring_mask;
+        for (int k = max(op_before, op - rmask - 1) + lane; k < op; k += 32) ring[k & rmask] = dst[k];
         __syncwarp();
     }
 }
 
 // ---- a decoder warp: batches d, d + kTeamDecWarps, ...
-__device__ __forceinline__ void team_decode(TeamShared* ts, const uint8_t* __restrict__ src, int cap, int dsz, int d, int lane)
+__device__ __forceinline__ void team_decode(TeamShared* ts, const uint8_t* __restrict__ src, int cap, int dsz, int d, int lane,
+                                            int nw)
 {
     const bool check_offset = dsz < 65536;
+    const int window = (ts->ring_mask + 1) >> 1;
     for (int b = d;; b += kTeamDecWarps) {
         for (int spins = 0;; spins++) {
             const int c = team_poll(ts, &ts->sb_head, b, lane);
@@ -768,10 +775,10 @@ __device__ __forceinline__ void team_decode(TeamShared* ts, const uint8_t* __res
             const int code = -__shfl_sync(FULL_MASK, my_ipn, f) - 1;
             if (lane == 0) atomicMin(&ts->err, ((unsigned long long)(uint32_t)(b * 32 + f) << 32) | (uint32_t)code);
         } else {
-            // the ring holds 64 KiB: nothing may be published more than kTeamWindow ahead of the oldest unfinished byte
+            // nothing may be published more than half a ring ahead of the oldest unfinished byte
             // (everything between the last slot and this batch is decode_one's, hence finished)
             const int pend = ts->pend;
-            if (!team_wait(ts, ts->prog, kTeamCopyWarps, min(out1 - kTeamWindow, pend), lane)) return;
+            if (!team_wait(ts, ts->prog, nw, min(out1 - window, pend), lane)) return;
             // slots of at most 1024 output bytes (the start bitmap's reach)
             for (int first = 0; first < nseq;) {
                 const int base = __shfl_sync(FULL_MASK, o, first);
@@ -780,7 +787,7 @@ __device__ __forceinline__ void team_decode(TeamShared* ts, const uint8_t* __res
                 const bool mine = lane >= first && lane < first + cnt;
                 const int end = __shfl_sync(FULL_MASK, o + span, first + cnt - 1);
                 const int h = ts->head;
-                if (!team_wait(ts, ts->passed, kTeamCopyWarps, h - kTeamSlots + 1, lane)) return;
+                if (!team_wait(ts, ts->passed, nw, h - kTeamSlots + 1, lane)) return;
                 TeamSlot& sl = ts->slot[h % kTeamSlots];
                 const int orel = o - base;
                 sl.bits[lane] = 0;
@@ -811,9 +818,11 @@ __device__ __forceinline__ void team_decode(TeamShared* ts, const uint8_t* __res
 // ---- a copy warp: takes every published slot in order and produces the chunks dealt to it
 template <bool kDict>
 __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restrict__ src, uint8_t* dst,
-                                          const uint8_t* __restrict__ dict, int dsz, uint8_t* ring, int w, int lane, int dbg)
+                                          const uint8_t* __restrict__ dict, int dsz, uint8_t* ring, int w, int nw, int lane, int dbg)
 {
     int known = 0;                                  // every output byte below this is known to be written
+    const int rmask = ts->ring_mask;
+    const uint32_t window = (uint32_t)(rmask + 1) >> 1;
     for (int k = 0;; k++) {
         for (int spins = 0;; spins++) {
             const int c = team_poll(ts, &ts->head, k, lane);
@@ -837,12 +846,12 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
         const int len = out1 - out0;
         const int nch = (len + 31) >> 5;
         // chunks are dealt by where they lie in the output, so consecutive chunks go to different warps across slots too
-        int j = (w - (out0 >> 5)) % kTeamCopyWarps;
-        if (j < 0) j += kTeamCopyWarps;
+        int j = (w - (out0 >> 5)) % nw;
+        if (j < 0) j += nw;
         __syncwarp();
         if (lane == 0) ts->prog[w] = j < nch ? out0 + 32 * j : out1;
         if (dbg & 1) j = nch;                        // measurements: everything but the copy
-        for (; j < nch; j += kTeamCopyWarps) {
+        for (; j < nch; j += nw) {
             const int c = 32 * j;
             const int xr = c + lane;                                                        // byte position relative to out0
             const uint32_t sbits = __shfl_sync(FULL_MASK, my_bits, j);
@@ -856,17 +865,17 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
             const bool fwd = live && !is_lit && sr >= c;                                    // source inside this chunk
             const int s = out0 + sr;
             uint32_t val = 0;
-            if (live && is_lit) val = src[kp + d];                                          // literals wait for nobody
+            if (live && is_lit && !(dbg & 4)) val = src[kp + d];                            // literals wait for nobody
             // the match sources of this chunk that other chunks produce
             const bool extn = live && !is_lit && !fwd && s >= 0;
             const int need = __reduce_max_sync(FULL_MASK, extn ? s + 1 : 0);
             if (need > known && !(dbg & 2)) {
-                if (!team_wait(ts, ts->prog, kTeamCopyWarps, need, lane)) return;
+                if (!team_wait(ts, ts->prog, nw, need, lane)) return;
                 known = need;
             }
             if (live && !is_lit && !fwd) {
                 if (kDict && s < 0) val = dict[dsz + s];
-                else val = (ka >> 16) >= (uint32_t)kTeamWindow ? dst[s] : ring[s & 0xFFFF];
+                else val = (ka >> 16) >= window ? dst[s] : ring[s & rmask];
             }
             if (__any_sync(FULL_MASK, fwd)) {
                 int root = fwd ? (sr - c) : lane;
@@ -876,12 +885,12 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
             }
             if (live) {
                 dst[out0 + xr] = (uint8_t)val;
-                ring[(out0 + xr) & 0xFFFF] = (uint8_t)val;
+                ring[(out0 + xr) & rmask] = (uint8_t)val;
             }
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
-                ts->prog[w] = j + kTeamCopyWarps < nch ? out0 + 32 * (j + kTeamCopyWarps) : out1;
+                if (!(dbg & 8)) __threadfence_block();        // dbg 8: measurements, what the fence costs
+                ts->prog[w] = j + nw < nch ? out0 + 32 * (j + nw) : out1;
             }
         }
         __syncwarp();
@@ -892,23 +901,29 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
     }
 }
 
-template <bool kDict>
-__global__ void __launch_bounds__(kTeamThreads)
-lz4_decompress_team_kernel(DecodeArgs a, int dbg)
+
+constexpr int kTeamStateBytes = (int)((sizeof(TeamShared) + 15) & ~size_t(15));
+
+// kPair: two teams per SM (at most 8 copy warps each, 64 registers per thread)
+template <bool kDict, bool kPair>
+__global__ void __launch_bounds__(kPair ? (kTeamFirstCopy + 8) * 32 : kTeamThreads, kPair ? 2 : 1)
+lz4_decompress_team_kernel(DecodeArgs a, int ring_bytes, int dbg)
 {
-    extern __shared__ __align__(16) uint8_t dyn_smem[];              // 64 KiB output window, then the team's state
-    uint8_t* ring = dyn_smem;
-    TeamShared* ts = reinterpret_cast<TeamShared*>(dyn_smem + 65536);
+    extern __shared__ __align__(16) uint8_t dyn_smem[];              // the team's state, then the output window
+    TeamShared* ts = reinterpret_cast<TeamShared*>(dyn_smem);
+    uint8_t* ring = dyn_smem + kTeamStateBytes;
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const uint32_t b = blockIdx.x;
+    const int nwarps = (int)(blockDim.x >> 5);
+    const int nw = nwarps - kTeamFirstCopy;                          // copy warps of this launch
 
     if (threadIdx.x < kTeamCopyWarps) { ts->prog[threadIdx.x] = 0; ts->passed[threadIdx.x] = 0; }
     if (threadIdx.x < kTeamDecWarps) ts->dec_next[threadIdx.x] = threadIdx.x;
     if (threadIdx.x < kTeamTabs) ts->tab_ready[threadIdx.x] = -1;
     if (threadIdx.x == 0) {
         ts->err = ~0ull; ts->parser_sw = 0; ts->sb_head = 0; ts->dec_done = 0; ts->head = 0; ts->pend = 0;
-        ts->quit = 0; ts->stall = 0; ts->hash_state = 0;
+        ts->quit = 0; ts->stall = 0; ts->hash_state = 0; ts->ring_mask = ring_bytes - 1;
     }
     __syncthreads();
 
@@ -933,7 +948,7 @@ lz4_decompress_team_kernel(DecodeArgs a, int dbg)
         verify = a.verify_checksum != 0;
     }
 
-    if (warp == kTeamWarps - 1) {
+    if (warp == kTeamFirstCopy - 1) {
         // checksum warp (blk/frame.go:114-127): runs beside the decode, its verdict outranks the decoder's
         if (verify) {
             const uint32_t want = load_le32(payload + csize);
@@ -946,9 +961,10 @@ lz4_decompress_team_kernel(DecodeArgs a, int dbg)
 
     if (stored) {
         // straight copy (async/reader.go:149-164), a slice per warp
-        if (warp < kTeamWarps - 1) {
-            const uint32_t piece = ((csize + kTeamWarps - 2) / (kTeamWarps - 1) + 511u) & ~511u;
-            const uint32_t lo = min(csize, (uint32_t)warp * piece), hi = min(csize, lo + piece);
+        if (warp != kTeamFirstCopy - 1) {
+            const int cw = warp < kTeamFirstCopy ? warp : warp - 1;            // copying warps, numbered without the checksum warp
+            const uint32_t piece = ((csize + (uint32_t)nwarps - 2u) / ((uint32_t)nwarps - 1u) + 511u) & ~511u;
+            const uint32_t lo = min(csize, (uint32_t)cw * piece), hi = min(csize, lo + piece);
             if (hi > lo) warp_copy(out + lo, payload + lo, hi - lo, lane);
         }
         __syncthreads();
@@ -957,7 +973,7 @@ lz4_decompress_team_kernel(DecodeArgs a, int dbg)
     }
 
     if (warp == 0) {
-        int32_t r = team_parse<kDict>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane, ring, ts);
+        int32_t r = team_parse<kDict>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane, ring, ts, nw);
         __syncwarp();
         if (lane == 0) { __threadfence_block(); ts->quit = 1; }
         if (verify) {
@@ -974,15 +990,19 @@ lz4_decompress_team_kernel(DecodeArgs a, int dbg)
     } else if (warp <= kTeamTabWarps) {
         if (csize > 0 && a.dst_cap > 0) team_tables(ts, payload, (int)csize, warp - 1, lane);
     } else if (warp <= kTeamTabWarps + kTeamDecWarps) {
-        team_decode(ts, payload, (int)a.dst_cap, (int)a.dict_size, warp - 1 - kTeamTabWarps, lane);
-    } else {
-        team_copy<kDict>(ts, payload, out, a.dict, (int)a.dict_size, ring, warp - 1 - kTeamTabWarps - kTeamDecWarps, lane, dbg);
+        team_decode(ts, payload, (int)a.dst_cap, (int)a.dict_size, warp - 1 - kTeamTabWarps, lane, nw);
+    } else if (warp >= kTeamFirstCopy) {
+        team_copy<kDict>(ts, payload, out, a.dict, (int)a.dict_size, ring, warp - kTeamFirstCopy, nw, lane, dbg);
     }
 }
 
 constexpr uint32_t kRingBlocks = 1024;          // launches with fewer blocks than this use the ring kernel
 constexpr int kRingBytes = 65536;
-constexpr int kTeamSmem = 65536 + (int)sizeof(TeamShared);
+constexpr int kTeamSmem = 131072 + kTeamStateBytes;
+int g_sm_count = 148;
+int g_team_pair = -1;                           // two teams per SM: -1 when the launch has more blocks than SMs, 0 never, 1 always
+int g_team_ring = 65536;                        // output window of a lone team, bytes (PLZ4CU_TEAM_RING: 65536 or 131072)
+int g_team_copy = 8;                            // copy warps per team (PLZ4CU_TEAM_COPY)
 int g_team_dbg = 0;                             // PLZ4CU_TEAM_DBG: measurement switches of the team kernel (wrong output)
 int g_team = 1;                                 // PLZ4CU_TEAM=0: few large blocks go back to one warp per block (measurements);
                                                 // =2: every launch below kRingBlocks blocks takes the team kernel (tests)
@@ -993,11 +1013,22 @@ cudaError_t configure_decompress()
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lz4_decompress_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lz4_decompress_team_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem);
+    e = cudaFuncSetAttribute(lz4_decompress_team_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lz4_decompress_team_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lz4_decompress_team_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem);
+    if (e != cudaSuccess) return e;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (const char* v = getenv("PLZ4CU_TEAM_PAIR")) g_team_pair = atoi(v);
+    if (const char* v = getenv("PLZ4CU_TEAM_RING")) { const int r = atoi(v); if (r == 65536 || r == 131072) g_team_ring = r; }
     if (const char* v = getenv("PLZ4CU_TEAM")) g_team = atoi(v);
     if (const char* v = getenv("PLZ4CU_TEAM_DBG")) g_team_dbg = atoi(v);
-    return cudaFuncSetAttribute(lz4_decompress_team_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem);
+    if (const char* v = getenv("PLZ4CU_TEAM_COPY")) { const int c = atoi(v); if (c >= 1 && c <= kTeamCopyWarps) g_team_copy = c; }
+    return cudaFuncSetAttribute(lz4_decompress_team_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem);
 }
 
 cudaError_t launch_decompress(const DecodeArgs& a, cudaStream_t stream)
@@ -1005,9 +1036,18 @@ cudaError_t launch_decompress(const DecodeArgs& a, cudaStream_t stream)
     if (a.nblk == 0) return cudaSuccess;
     if (g_team && a.nblk < kRingBlocks && (a.dst_cap > 65536u || g_team == 2)) {
         // few, large blocks: one CTA per block (parser warp, copy warps, checksum warp), up to 3 CTAs per SM
-        dim3 grid(a.nblk), block(kTeamThreads);
-        if (a.dict_size > 0) lz4_decompress_team_kernel<true><<<grid, block, kTeamSmem, stream>>>(a, g_team_dbg);
-        else lz4_decompress_team_kernel<false><<<grid, block, kTeamSmem, stream>>>(a, g_team_dbg);
+        const bool pair = g_team_pair < 0 ? a.nblk > (uint32_t)g_sm_count : g_team_pair != 0;
+        const int ncopy = pair ? min(g_team_copy, 8) : g_team_copy;
+        const int ring_bytes = pair ? 32768 : g_team_ring;
+        const size_t smem = (size_t)kTeamStateBytes + (size_t)ring_bytes;
+        dim3 grid(a.nblk), block((kTeamFirstCopy + ncopy) * 32);
+        if (pair) {
+            if (a.dict_size > 0) lz4_decompress_team_kernel<true, true><<<grid, block, smem, stream>>>(a, ring_bytes, g_team_dbg);
+            else lz4_decompress_team_kernel<false, true><<<grid, block, smem, stream>>>(a, ring_bytes, g_team_dbg);
+        } else {
+            if (a.dict_size > 0) lz4_decompress_team_kernel<true, false><<<grid, block, smem, stream>>>(a, ring_bytes, g_team_dbg);
+            else lz4_decompress_team_kernel<false, false><<<grid, block, smem, stream>>>(a, ring_bytes, g_team_dbg);
+        }
         return cudaGetLastError();
     }
     if (a.nblk < kRingBlocks && a.dst_cap > 65536u) {

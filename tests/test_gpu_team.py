@@ -108,10 +108,13 @@ def test_large_block_dictionary_decode(gpu, port):
         assert out[i, : len(s)].tobytes() == s
 
 
-def test_whole_decode_suite_through_the_team_kernel():
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_whole_decode_suite_through_the_team_kernel(pair):
     """PLZ4CU_TEAM=2 sends every launch below 1024 blocks through the team kernel, whatever the capacity: the one-warp
-    decoder's own parity suite (capacity edges, 4500 corrupted streams, dictionaries) must pass unchanged."""
-    env = dict(os.environ, PLZ4CU_TEAM="2")
-    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_decompress.py"],
+    decoder's own parity suite (capacity edges, 4500 corrupted streams, dictionaries) must pass unchanged, and so must
+    the tests above, with one team per SM (64 KiB output window) and with two (32 KiB)."""
+    env = dict(os.environ, PLZ4CU_TEAM="2", PLZ4CU_TEAM_PAIR=pair)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k", "not whole_decode_suite",
+                        "tests/test_gpu_decompress.py", "tests/test_gpu_team.py"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
