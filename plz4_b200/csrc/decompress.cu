@@ -460,8 +460,8 @@ __device__ __forceinline__ bool team_wait(TeamShared* ts, const volatile int* ar
 {
     for (int spins = 0;; spins++) {
         const int v = lane < cnt ? arr[lane] : 0x7FFFFFFF;
-        const int st = ts->stall;
         if (__all_sync(FULL_MASK, v >= need)) break;
+        const int st = ts->stall;
         if (__any_sync(FULL_MASK, st != 0) || spins > kTeamSpinLimit) {
             if (lane == 0) ts->stall = 1;
             return false;
@@ -1002,7 +1002,7 @@ constexpr int kTeamSmem = 131072 + kTeamStateBytes;
 int g_sm_count = 148;
 int g_team_pair = -1;                           // two teams per SM: -1 when the launch has more blocks than SMs, 0 never, 1 always
 int g_team_ring = 65536;                        // output window of a lone team, bytes (PLZ4CU_TEAM_RING: 65536 or 131072)
-int g_team_copy = 8;                            // copy warps per team (PLZ4CU_TEAM_COPY)
+int g_team_copy = 16;                           // copy warps of a lone team (PLZ4CU_TEAM_COPY); paired teams have 8
 int g_team_dbg = 0;                             // PLZ4CU_TEAM_DBG: measurement switches of the team kernel (wrong output)
 int g_team = 1;                                 // PLZ4CU_TEAM=0: few large blocks go back to one warp per block (measurements);
                                                 // =2: every launch below kRingBlocks blocks takes the team kernel (tests)

@@ -81,7 +81,7 @@ res["config0_256MiB_4MiB_blocks_bx_cx_streams"] = {
     "gpu_write_gbs_no_content_checksum": round(len(raw) / tw_n / 1e9, 2), "gpu_read_gbs_no_content_checksum": round(len(raw) / tr_n / 1e9, 2),
     "cpu_compress_gbs": round(cc, 2), "cpu_decompress_gbs": round(cd, 2), "cpu_ratio": round(cr, 4),
     "note": "NewWriter/NewReader over in-memory C endpoints, pageable caller buffers; CPU columns are block-level (no stream layer, no content checksum); "
-            "decode of 4 MiB blocks is one warp per block (64 blocks here): DESIGN.md 6b"}
+            "decode of 4 MiB blocks is one CTA per block (64 blocks here): DESIGN.md 4.1b"}
 
 # ---- configs[2]: decode reference-produced frames (4 MiB blocks, bx) from random WithReadOffset starts
 from oracle import frame_oracle as F
