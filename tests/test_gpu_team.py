@@ -108,6 +108,36 @@ def test_large_block_dictionary_decode(gpu, port):
         assert out[i, : len(s)].tobytes() == s
 
 
+def test_long_literal_runs_jump_over_superwindows(gpu, codec):
+    """Random islands inside compressible text become literal runs of up to 70 KB: decode_one carries the parser over
+    several 4 KiB superwindows at once and the table warps have to skip ahead with it."""
+    rng = random.Random(7)
+    blocks = []
+    for it in range(10):
+        parts, total = [], 0
+        while total < 500000:
+            if rng.random() < 0.5:
+                p = rng.randbytes(rng.choice([100, 4000, 4200, 9000, 20000, 70000]))
+            else:
+                p = make("log", rng.choice([3000, 50000, 150000]), seed=it)
+            parts.append(p)
+            total += len(p)
+        blocks.append(b"".join(parts))
+    comp = [codec.compress(b) for b in blocks]
+    cap = max(len(b) for b in blocks)
+    buf, off = b"".join(comp), np.cumsum([0] + [len(c) for c in comp])[:-1]
+    out, res = gpu.decompress_batch(buf, off, cap, raw_len=[len(c) for c in comp])
+    for i, b in enumerate(blocks):
+        assert res[i] == len(b), (i, res[i], len(b))
+        assert out[i, : len(b)].tobytes() == b, i
+    # the same streams cut short / with too little room must give liblz4's codes
+    for i, c in enumerate(comp[:4]):
+        for cut, room in ((len(c) // 2, cap), (len(c), len(blocks[i]) - 1), (len(c) - 1, cap)):
+            want, _ = codec.decompress(c[:cut], room)
+            _, r = gpu.decompress_batch(c[:cut], [0], room, raw_len=[cut])
+            assert r[0] == want, (i, cut, room, r[0], want)
+
+
 @pytest.mark.parametrize("pair", ["0", "1"])
 def test_whole_decode_suite_through_the_team_kernel(pair):
     """PLZ4CU_TEAM=2 sends every launch below 1024 blocks through the team kernel, whatever the capacity: the one-warp
