@@ -394,7 +394,7 @@ lz4_decompress_kernel(DecodeArgs a)
 constexpr int kTeamTabs = 3;                                    // superwindow tables; table warp t owns table t and prepares
 constexpr int kTeamTabWarps = kTeamTabs;                        // superwindows t, t + 3, ...: two are ahead of the parser's
 constexpr int kTeamDecWarps = 3;
-constexpr int kTeamCopyWarps = 16;                              // at most; a launch chooses how many (PLZ4CU_TEAM_COPY)
+constexpr int kTeamCopyWarps = 16;                              // at most; a launch chooses 4, 8 or 16 (PLZ4CU_TEAM_COPY)
 constexpr int kTeamFirstCopy = 1 + kTeamTabWarps + kTeamDecWarps + 1;   // warps: parser, tables, decoders, checksum, copy...
 constexpr int kTeamThreads = (kTeamFirstCopy + kTeamCopyWarps) * 32;
 constexpr int kTeamSeqRing = 64;                                // batches between parser and decoders
@@ -815,14 +815,19 @@ __device__ __forceinline__ void team_decode(TeamShared* ts, const uint8_t* __res
     }
 }
 
-// ---- a copy warp: takes every published slot in order and produces the chunks dealt to it
+// ---- a copy warp: takes every published slot in order and produces the chunks dealt to it.
+// Chunks are the 32-byte-aligned pieces of the OUTPUT (absolute positions), dealt round-robin: chunk i belongs to warp
+// i mod nw whatever slot its bytes come in (a chunk that straddles two slots is produced in two parts by the same warp).
+// So the owner of any earlier output byte is known from its position alone, and a lane waits for exactly the warp that
+// produces its match source (prog[owner] past that byte) instead of for every chunk below it.
 template <bool kDict>
 __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restrict__ src, uint8_t* dst,
                                           const uint8_t* __restrict__ dict, int dsz, uint8_t* ring, int w, int nw, int lane, int dbg)
 {
-    int known = 0;                                  // every output byte below this is known to be written
     const int rmask = ts->ring_mask;
     const uint32_t window = (uint32_t)(rmask + 1) >> 1;
+    const uint32_t lmask = (2u << lane) - 1u;
+    const int wmask = nw - 1;                       // nw is a power of two
     for (int k = 0;; k++) {
         for (int spins = 0;; spins++) {
             const int c = team_poll(ts, &ts->head, k, lane);
@@ -844,34 +849,45 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
         const uint32_t my_bits = sl.bits[lane];
         const int orel = lane < nseq ? (int)(packA & 0x3FFu) : 0x7FFFFFF;   // sequences outside the slot start "never"
         const int len = out1 - out0;
-        const int nch = (len + 31) >> 5;
-        // chunks are dealt by where they lie in the output, so consecutive chunks go to different warps across slots too
-        int j = (w - (out0 >> 5)) % nw;
-        if (j < 0) j += nw;
+        const int a = out0 & 31;                    // the slot starts this far into its first chunk
+        const int chunk0 = out0 >> 5;               // absolute index of that chunk
+        const int np = (a + len + 31) >> 5;         // chunks the slot touches
+        int p = (w - chunk0) & wmask;               // my first one
         __syncwarp();
-        if (lane == 0) ts->prog[w] = j < nch ? out0 + 32 * j : out1;
-        if (dbg & 1) j = nch;                        // measurements: everything but the copy
-        for (; j < nch; j += nw) {
-            const int c = 32 * j;
-            const int xr = c + lane;                                                        // byte position relative to out0
-            const uint32_t sbits = __shfl_sync(FULL_MASK, my_bits, j);
-            const int q = __popc(__ballot_sync(FULL_MASK, orel < c)) - 1 + __popc(sbits & ((2u << lane) - 1u));
+        if (lane == 0) ts->prog[w] = p < np ? max(out0, (chunk0 + p) << 5) : out1;
+        if (dbg & 1) p = np;                         // measurements: everything but the copy
+        for (; p < np; p += nw) {
+            const int c = 32 * p - a;                                                       // chunk start relative to out0 (< 0: before the slot)
+            const int xr = c + lane;                                                        // my byte, relative to out0
+            const bool live = xr >= 0 && xr < len;
+            // sequence starts inside the chunk: 32 bits of the slot's bitmap from bit c on
+            const int wi = c >> 5;                                                          // floor: -1 for the straddling first chunk
+            const uint32_t lo = __shfl_sync(FULL_MASK, my_bits, wi & 31), hi = __shfl_sync(FULL_MASK, my_bits, (wi + 1) & 31);
+            const uint32_t sbits = __funnelshift_r(wi >= 0 ? lo : 0u, wi + 1 <= 31 ? hi : 0u, (uint32_t)(c & 31));
+            const int q = __popc(__ballot_sync(FULL_MASK, orel < c)) - 1 + __popc(sbits & lmask);
             const uint32_t ka = __shfl_sync(FULL_MASK, packA, q);
             const int kp = __shfl_sync(FULL_MASK, my_litpos, q);
-            const bool live = xr < len;
             const int d = xr - (int)(ka & 0x3FFu);                                          // byte index inside the sequence
             const bool is_lit = d < (int)((ka >> 10) & 63u);
             const int sr = xr - (int)(ka >> 16);                                            // match source, relative to out0
-            const bool fwd = live && !is_lit && sr >= c;                                    // source inside this chunk
+            const bool fwd = live && !is_lit && sr >= max(c, 0);                            // source inside this chunk's part of the slot
             const int s = out0 + sr;
             uint32_t val = 0;
             if (live && is_lit && !(dbg & 4)) val = src[kp + d];                            // literals wait for nobody
-            // the match sources of this chunk that other chunks produce
+            // match sources that other chunks produce: wait for the warp that owns each of them
             const bool extn = live && !is_lit && !fwd && s >= 0;
-            const int need = __reduce_max_sync(FULL_MASK, extn ? s + 1 : 0);
-            if (need > known && !(dbg & 2)) {
-                if (!team_wait(ts, ts->prog, nw, need, lane)) return;
-                known = need;
+            if (__any_sync(FULL_MASK, extn) && !(dbg & 2)) {
+                const volatile int* theirs = &ts->prog[(s >> 5) & wmask];
+                for (int spins = 0;; spins++) {
+                    const bool ok = !extn || *theirs > s;
+                    if (__all_sync(FULL_MASK, ok)) break;
+                    const int st = ts->stall;
+                    if (__any_sync(FULL_MASK, st != 0) || spins > kTeamSpinLimit) {
+                        if (lane == 0) ts->stall = 1;
+                        return;
+                    }
+                }
+                __threadfence_block();
             }
             if (live && !is_lit && !fwd) {
                 if (kDict && s < 0) val = dict[dsz + s];
@@ -889,8 +905,8 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
             }
             __syncwarp();
             if (lane == 0) {
-                if (!(dbg & 8)) __threadfence_block();        // dbg 8: measurements, what the fence costs
-                ts->prog[w] = j + nw < nch ? out0 + 32 * (j + nw) : out1;
+                __threadfence_block();
+                ts->prog[w] = p + nw < np ? (chunk0 + p + nw) << 5 : out1;
             }
         }
         __syncwarp();
@@ -900,7 +916,6 @@ __device__ __forceinline__ void team_copy(TeamShared* ts, const uint8_t* __restr
         }
     }
 }
-
 
 constexpr int kTeamStateBytes = (int)((sizeof(TeamShared) + 15) & ~size_t(15));
 
@@ -1027,7 +1042,7 @@ cudaError_t configure_decompress()
     if (const char* v = getenv("PLZ4CU_TEAM_RING")) { const int r = atoi(v); if (r == 65536 || r == 131072) g_team_ring = r; }
     if (const char* v = getenv("PLZ4CU_TEAM")) g_team = atoi(v);
     if (const char* v = getenv("PLZ4CU_TEAM_DBG")) g_team_dbg = atoi(v);
-    if (const char* v = getenv("PLZ4CU_TEAM_COPY")) { const int c = atoi(v); if (c >= 1 && c <= kTeamCopyWarps) g_team_copy = c; }
+    if (const char* v = getenv("PLZ4CU_TEAM_COPY")) { const int c = atoi(v); if (c == 4 || c == 8 || c == 16) g_team_copy = c; }
     return cudaFuncSetAttribute(lz4_decompress_team_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem);
 }
 
