@@ -402,6 +402,7 @@ constexpr int kTeamSlots = 16;                                  // batches betwe
 // The output window in shared memory is a ring of R bytes (64 KiB with one team per SM, 32 KiB when two teams share an SM).
 // At most R/2 output bytes may be in flight, and matches reaching back R/2 or more read global memory instead of the
 // ring: then no chunk in flight can overwrite a ring byte another chunk in flight still reads.
+constexpr unsigned kTeamBackoffNs = 320;                        // pause between polls of a table warp that is ahead of the parse
 constexpr int kTeamSpinLimit = 1 << 25;                         // watchdog: a stalled team reports PLZ4CU_E_STALL, it never hangs
 constexpr int kSwBytes = 4096;                                  // superwindow
 constexpr int kSwSlack = 128;                                   // bytes past it a header may touch (<= 68)
@@ -510,6 +511,8 @@ __device__ __forceinline__ void team_tables(TeamShared* ts, const uint8_t* __res
                 if (lane == 0) ts->stall = 1;
                 return;
             }
+            __nanosleep(kTeamBackoffNs);            // tables are two superwindows ahead: no hurry, and a polling warp takes
+                                                    // issue slots from the warps it waits for
         }
         __threadfence_block();
         uint32_t* const ex = ts->tab[k % kTeamTabs];
