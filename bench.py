@@ -424,7 +424,18 @@ def run_gpu(args) -> None:
         dist.destroy_process_group()
 
 
+def _keep_stdout_for_the_line():
+    """Native libraries write to file descriptor 1 too (NCCL prints its version banner there): point fd 1 at stderr for
+    the duration of the run and give `print` the real stdout, so that stdout carries the one JSON line and nothing else."""
+    import sys
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
+    _keep_stdout_for_the_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
