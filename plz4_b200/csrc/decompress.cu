@@ -1052,7 +1052,9 @@ cudaError_t configure_decompress()
 cudaError_t launch_decompress(const DecodeArgs& a, cudaStream_t stream)
 {
     if (a.nblk == 0) return cudaSuccess;
-    if (g_team && a.nblk < kRingBlocks && (a.dst_cap > 65536u || g_team == 2)) {
+    // (blocks beyond 32 MiB — raw-block API only — stay with one warp: a single sequence there can run for longer than the
+    // team's watchdog allows its other warps to wait)
+    if (g_team && a.nblk < kRingBlocks && (a.dst_cap > 65536u || g_team == 2) && a.dst_cap <= (32u << 20)) {
         // few, large blocks: one CTA per block (parser warp, copy warps, checksum warp), up to 3 CTAs per SM
         const bool pair = g_team_pair < 0 ? a.nblk > (uint32_t)g_sm_count : g_team_pair != 0;
         const int ncopy = pair ? min(g_team_copy, 8) : g_team_copy;
