@@ -27,6 +27,13 @@ def test_header_cites_reference_lines():
         assert needle in text
 
 
+def test_per_block_codes_agree_between_header_and_mirror():
+    """The negative out_len codes are part of the boundary: the ctypes mirror must carry the header's values."""
+    text = open(os.path.join(ROOT, "include", "plz4cu.h")).read()
+    codes = {m.group(1): -int(m.group(2), 16) for m in re.finditer(r"#define (PLZ4CU_E_\w+)\s+\(\(int32_t\)-0x([0-9A-Fa-f]+)\)", text)}
+    assert codes == {"PLZ4CU_E_BLOCKHASH": _lib.E_BLOCKHASH, "PLZ4CU_E_OVERFLOW": _lib.E_OVERFLOW, "PLZ4CU_E_STALL": _lib.E_STALL}
+
+
 def test_compress_bound_matches_reference(port):
     L = _lib.lib()
     # block_test.go:338-353 (monotonic) + lz4.h:215 values quoted in SURVEY.md a14
