@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libplz4cu.so")
-SOURCES = ["engine.cu", "compress.cu", "decompress.cu", "misc.cu", "frame_index.cu", "host_stream.cu"]
-HEADERS = ["common.cuh", "kernels.h", "logtext.h", "host_stream.h", os.path.join("..", "..", "include", "plz4cu.h")]
+SOURCES = ["engine.cu", "compress.cu", "compress_cta.cu", "decompress.cu", "misc.cu", "frame_index.cu", "host_stream.cu"]
+HEADERS = ["common.cuh", "kernels.h", "logtext.h", os.path.join("..", "..", "include", "plz4cu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

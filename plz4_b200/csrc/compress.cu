@@ -496,6 +496,7 @@ lz4_stitch_kernel(FragArgs a)
             carry = (int)a.frag_tail[w];
             pos += nf;
         }
+        if (pos != n_blk) ok = false;                      // fewer fragments than the block needs (never, by launch_compress)
         if (ok && op + 1 + (carry >= 15 ? ext_bytes(carry - 15) : 0) + carry > cap) ok = false;
         if (lane == 0) { s_end = op; s_tail = carry; s_ok = ok ? 1 : 0; }
     }
@@ -605,6 +606,7 @@ cudaError_t launch_dict_build(const uint8_t* dict, uint32_t dict_size, int bits,
     return cudaGetLastError();
 }
 
+static int g_cta_min = 8192;      // blocks at least this long get a CTA each (compress_cta.cu); PLZ4CU_CTA_MIN, 0 = never
 static int g_hash_bits = 12;     // 7 KiB of table per warp: 28 resident warps per SM against 12 with liblz4's 13 bits;
                                  // the one-step lazy parse more than pays the ratio back (profiles/r01_sweep.txt)
 
@@ -635,6 +637,7 @@ cudaError_t configure_compress()
         int v = atoi(e);
         if (v >= 11 && v <= 13) g_hash_bits = v;
     }
+    if (const char* e = getenv("PLZ4CU_CTA_MIN")) g_cta_min = atoi(e);
     if (const char* e = getenv("PLZ4CU_BACK")) {
         int v = atoi(e);
         cudaError_t err = cudaMemcpyToSymbol(g_back_dev, &v, sizeof v);
@@ -676,12 +679,17 @@ static cudaError_t launch_frag(const FragArgs& fa, uint32_t nwarps, cudaStream_t
 cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
 {
     if (a.nblk == 0) return cudaSuccess;
-    if (a.dst_cap > (uint32_t)kFragBytes + kFragBytes / 255u + 16u && a.dict_size == 0 &&
-        (a.dst_cap + kFragBytes - 1) / kFragBytes <= (uint32_t)kMaxFrags + 1) {
+    const uint32_t max_len = a.max_src_len ? a.max_src_len : a.dst_cap;
+    if (a.dict_size == 0 && max_len <= (uint32_t)kFragBytes && g_cta_min > 0 && max_len >= (uint32_t)g_cta_min)
+        return launch_compress_cta(a, stream);
+    // fragments are sized from the data, not from the room: the caller may offer less room than a block is long
+    // (plz4_block.go:100-109 WithBlockDst; the block then compresses into it or is refused, lz4.c:1382)
+    const uint32_t frags = (max_len + kFragBytes - 1) / kFragBytes;
+    if (max_len > (uint32_t)kFragBytes && a.dict_size == 0 && frags <= (uint32_t)kMaxFrags) {
         // large blocks: fragment-parallel encode + stitch; scratch comes from the stream-ordered allocator
         FragArgs fa{};
         fa.e = a;
-        fa.frags_per_block = (a.dst_cap + kFragBytes - 1) / kFragBytes;
+        fa.frags_per_block = frags;
         fa.frag_stride = (uint32_t)((kFragBytes + kFragBytes / 255 + 16 + 15) & ~15);
         const uint64_t nfrag = (uint64_t)a.nblk * fa.frags_per_block;
         void* scratch = nullptr;

@@ -1,0 +1,686 @@
+// compress_cta.cu — LZ4 level-1 block encode, one CTA per block of up to 64 KiB (sm_100a).
+//
+// Replaces, for a whole batch of independent blocks, what plz4 does per block on a goroutine:
+//   async/writer.go:232-282 compressLoop -> blk/blk.go:69-109 CompressToBlk
+//     -> compress/indie.go:66-74 -> clz4.go:31-45 -> lz4.c:930-1338 LZ4_compress_generic_validated
+//   plus the record framing (size word / stored fallback / xxh32 trailer) of blk/blk.go:87-106.
+//
+// The block is brought into shared memory ONCE by a TMA bulk copy (cp.async.bulk + mbarrier) and every later
+// access — hashing, candidate verification, match extension, literal copies — is a shared-memory access.
+// The CTA is a small dataflow machine of specialised warps, stages joined by mbarriers (parked waits):
+//   * indexer (1 warp): for EVERY position, in order, the most recent earlier position with the same hash
+//     (liblz4's hash4, lz4.c:777-783, 4096 slots): per 32 positions one table read + one table write, same-group
+//     duplicates resolved with match.any.  Output: prev[] for a tile of 1024 positions, into a ring.
+//   * parsers (6 warps, tiles round-robin): (1) verify every candidate of the tile (4 equal bytes) -> one
+//     32-bit map per lane; (2) every LANE parses its own 32 positions serially — greedy with a one-step lazy
+//     check, forward extension in 4-byte steps, backward extension, at most 8 matches — with no knowledge of
+//     its neighbours; matches may run past the lane's end; matches longer than 68 bytes are completed by the
+//     whole warp; (3) resolve: a prefix maximum over the lanes' match ends tells each lane where the parse
+//     of the lanes before it stops, what it must drop or trim, and where its first literal run begins; sizes
+//     are prefix-summed and every lane writes its own sequences into a staging tile; (4) the tile goes out with
+//     16-byte stores.  Entry state (covered-up-to, literal anchor, output offset) passes from tile to tile.
+//   * hasher (1 warp): block checksum (xxh32.ChecksumZero, xxh32/xxh32zero.go:238-280) over the payload, chunk
+//     by chunk as tiles complete; then last literals (lz4.c:1302-1329), stored fallback, size word, trailer.
+// The parse is not liblz4's (bytes differ, the reference decodes them; size within the tolerance pinned by
+// tests/test_gpu_compress.py): all positions enter the table, and the lazy step more than pays for the lanes'
+// independent starts (tools/parse_model.c is the CPU model the design was sized with).
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cstdlib>
+
+namespace plz4 {
+
+namespace {
+
+constexpr int kCtaThreads = 256;
+constexpr int kParsers = 6;                     // warps 1..6
+constexpr int kTile = 1024;                     // positions per tile: 32 lanes x 32 positions
+constexpr int kRing = 8;                        // tiles of prev[] the indexer may run ahead
+constexpr int kMaxTiles = 64;
+constexpr int kStage = 2048 + 64;               // staging bytes per parser warp
+constexpr int kLaneCap = 64;                    // a lane extends a match this far by itself
+constexpr int kLongLit = 48;                    // literal runs from this length on are copied by the whole warp
+constexpr uint32_t kNone = 0xFFFFu;
+constexpr int kWinPad = 32;
+constexpr int kHashChunk = 512;                 // bytes the hasher consumes per step (32 stripes)
+
+struct __align__(16) CtaSmem {
+    uint8_t win[65536 + kWinPad];               // the block
+    uint8_t stage[kParsers][kStage];
+    uint16_t table[4096];
+    uint16_t prev[kRing][kTile];
+    uint32_t recs[kParsers][8][32];             // [record][lane]: offset<<16 | min(len,2047)<<5 | start-b0
+    unsigned long long bar_load;
+    unsigned long long bar_full[kRing], bar_empty[kRing];
+    unsigned long long bar_entry[kMaxTiles + 1];      // [t]: entry state of tile t is published
+    unsigned long long bar_done[kMaxTiles];           // [t]: tile t's bytes are in global memory
+    int st_x[kMaxTiles + 1], st_anchor[kMaxTiles + 1], st_out[kMaxTiles + 1];
+    int latest_x;
+    int fail;
+    uint32_t hash_acc[32];                            // the hasher's running state, parked for the finish
+    int hash_done;
+};
+
+// ---------------------------------------------------------------- mbarrier / TMA plumbing
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// Parked wait for the phase of the given parity; a stall of seconds is a bug and ends the kernel instead of the box.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    const uint32_t a = smem_addr(bar);
+    long long t0 = 0;
+    for (uint32_t spins = 0;; spins++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spins == 64) t0 = clock64();
+        if (spins > 64 && (spins & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_bulk(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- small helpers
+
+// 4 bytes at byte position p of the window (two aligned words + funnel shift; reads up to p+7)
+__device__ __forceinline__ uint32_t ld4(const uint32_t* __restrict__ w32, int p)
+{
+    const int i = p >> 2;
+    return __funnelshift_r(w32[i], w32[i + 1], (uint32_t)(p & 3) * 8u);
+}
+
+__device__ __forceinline__ int ext_len(int rest) { return rest / 255 + 1; }     // bytes of a 255-run for a saturated nibble
+
+__device__ __forceinline__ int seq_size(int lit, int len)
+{
+    int s = 3 + lit;
+    if (lit >= 15) s += ext_len(lit - 15);
+    if (len >= 19) s += ext_len(len - 19);
+    return s;
+}
+
+__device__ __forceinline__ int warp_incl_max(int v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(FULL_MASK, v, d);
+        if (lane >= d) v = max(v, u);
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_incl_sum(int v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(FULL_MASK, v, d);
+        if (lane >= d) v += u;
+    }
+    return v;
+}
+
+// equal bytes of win[a..] and win[b..], at most `limit`, by the whole warp: 128 bytes per round
+__device__ __noinline__ int warp_count_equal(const uint32_t* __restrict__ w32, int a, int b, int limit, int lane)
+{
+    for (int total = 0; total < limit; total += 128) {
+        const int k = total + 4 * lane;
+        uint32_t x = 0;
+        if (k < limit) {
+            x = ld4(w32, a + k) ^ ld4(w32, b + k);
+            const int rem = limit - k;
+            if (rem < 4) x &= (1u << (8 * rem)) - 1u;
+        }
+        const uint32_t bal = __ballot_sync(FULL_MASK, x != 0);
+        if (bal) {
+            const int l = __ffs(bal) - 1;
+            const uint32_t xl = __shfl_sync(FULL_MASK, x, l);
+            return total + 4 * l + ((__ffs(xl) - 1) >> 3);
+        }
+    }
+    return limit;
+}
+
+// n bytes from shared memory (any alignment) to global memory (any alignment) by `nthr` threads: 16-byte stores on the
+// destination's alignment, bytes at the two ends
+__device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint8_t* src, int n, int tid, int nthr)
+{
+    if (n <= 0) return;
+    const int head = min(n, (int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
+    for (int k = tid; k < head; k += nthr) dst[k] = src[k];
+    const int nvec = (n - head) >> 4;
+    const uint8_t* s = src + head;
+    uint4* d = reinterpret_cast<uint4*>(dst + head);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(s) & ~uintptr_t(3));
+    for (int k = tid; k < nvec; k += nthr) {
+        const uint32_t w0 = sw[4 * k], w1 = sw[4 * k + 1], w2 = sw[4 * k + 2], w3 = sw[4 * k + 3];
+        uint4 v;
+        if (sh == 0) {
+            v = make_uint4(w0, w1, w2, w3);
+        } else {
+            const uint32_t w4 = sw[4 * k + 4];
+            v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+            v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+        }
+        d[k] = v;
+    }
+    for (int k = head + (nvec << 4) + tid; k < n; k += nthr) dst[k] = src[k];
+}
+
+// ---------------------------------------------------------------- indexer
+
+__device__ __forceinline__ void run_indexer(CtaSmem& S, int n, int ntiles, int lane)
+{
+    const uint32_t* __restrict__ w32 = reinterpret_cast<const uint32_t*>(S.win);
+    const int hash_end = n - 3;                               // 4 bytes exist at p < hash_end
+    for (int t = 0; t < ntiles; t++) {
+        const int slot = t % kRing;
+        mbar_wait(&S.bar_empty[slot], (((uint32_t)t / kRing) & 1u) ^ 1u);
+        uint16_t* __restrict__ pv = S.prev[slot];
+        const int tile_base = t * kTile;
+#pragma unroll 4
+        for (int g = 0; g < 32; g++) {
+            const int base = tile_base + g * 32;
+            const int p = base + lane;
+            const bool valid = p < hash_end;
+            uint32_t h = 0x10000u | (uint32_t)lane;           // lanes past the end never pair up
+            if (valid) h = (ld4(w32, p) * 2654435761u) >> 20;
+            const uint32_t same = __match_any_sync(FULL_MASK, h);
+            const int hi = 31 - __clz(same);
+            uint32_t old = kNone;
+            if (valid && lane == hi) {                        // the group's last occurrence replaces the table entry
+                old = S.table[h];
+                S.table[h] = (uint16_t)p;
+            }
+            old = __shfl_sync(FULL_MASK, old, hi);
+            const uint32_t lower = same & ((1u << lane) - 1u);
+            const uint32_t cand = lower ? (uint32_t)(base + 31 - __clz(lower)) : old;
+            pv[g * 32 + lane] = valid ? (uint16_t)cand : (uint16_t)kNone;
+            __syncwarp();                                     // the next group reads what this one wrote
+        }
+        if (lane == 0) mbar_arrive(&S.bar_full[slot]);
+    }
+}
+
+// ---------------------------------------------------------------- parsers
+
+struct TileCtx {
+    const uint32_t* w32;
+    const uint8_t* win;
+    int mf_end;        // a match may start at p < mf_end        (lz4.c:963: last match starts <= n-12)
+    int match_end;     // and must end at or before match_end    (last 5 bytes are literals)
+};
+
+// forward extension of a verified candidate: 4 bytes per step, at most kLaneCap bytes beyond the first four
+__device__ __forceinline__ void lane_extend(const uint32_t* __restrict__ w32, int p, int c, int lim, int& ml, bool& un)
+{
+    ml = 4;
+    un = false;
+    for (;;) {
+        if (ml >= lim) { ml = lim; break; }
+        const uint32_t x = ld4(w32, p + ml) ^ ld4(w32, c + ml);
+        if (x) {
+            ml = min(ml + ((__ffs(x) - 1) >> 3), lim);
+            break;
+        }
+        ml += 4;
+        if (ml >= 4 + kLaneCap) {
+            if (ml < lim) un = true; else ml = lim;
+            break;
+        }
+    }
+}
+
+__device__ __forceinline__ void put_ext_bytes(uint8_t* o, int rest)
+{
+    for (; rest >= 255; rest -= 255) *o++ = 255;
+    *o = (uint8_t)rest;
+}
+
+__device__ __forceinline__ void run_parser(CtaSmem& S, const EncodeArgs& a, uint8_t* payload, int n, int ntiles, int pw, int lane)
+{
+    TileCtx C;
+    C.w32 = reinterpret_cast<const uint32_t*>(S.win);
+    C.win = S.win;
+    C.mf_end = n - MFLIMIT + 1;
+    C.match_end = n - LASTLITERALS;
+    const uint32_t* __restrict__ w32 = C.w32;
+    const uint8_t* __restrict__ win = C.win;
+    const int cap = (int)a.dst_cap;
+    uint8_t* stage = S.stage[pw];
+    uint32_t(*recs)[32] = S.recs[pw];
+
+    for (int t = pw; t < ntiles; t += kParsers) {
+        const int slot = t % kRing;
+        const int tile_base = t * kTile;
+        const int b0 = tile_base + 32 * lane;
+        mbar_wait(&S.bar_full[slot], ((uint32_t)t / kRing) & 1u);
+        const uint16_t* __restrict__ pv = S.prev[slot];
+        const int xhint = *reinterpret_cast<volatile int*>(&S.latest_x);   // a lower bound of this tile's entry state
+
+        // ---- (1) verify the tile's candidates: lane g ends up with the map of positions b0 .. b0+31
+        uint32_t bits = 0;
+        if (xhint < tile_base + kTile) {
+#pragma unroll 4
+            for (int g = 0; g < 32; g++) {
+                const int p = tile_base + g * 32 + lane;
+                const uint32_t c = pv[g * 32 + lane];
+                bool okb = false;
+                if (c != kNone && p < C.mf_end) okb = ld4(w32, (int)c) == ld4(w32, p);
+                const uint32_t word = __ballot_sync(FULL_MASK, okb);
+                if (lane == g) bits = word;
+            }
+        }
+
+        // ---- (2) every lane parses its own 32 positions
+        int cnt = 0, last_q = 0, last_ml = 0, last_off = 0;
+        bool unfin = false;
+        {
+            int la = max(b0, xhint);
+            bits = (la - b0 >= 32) ? 0u : (bits & (0xFFFFFFFFu << (la - b0)));
+            while (bits) {
+                const int r = __ffs(bits) - 1;
+                int p = b0 + r;
+                int c = pv[p - tile_base];
+                int ml;
+                bool un;
+                lane_extend(w32, p, c, C.match_end - p, ml, un);
+                if (!un && r < 31 && ((bits >> (r + 1)) & 1u)) {          // one-step lazy: is the next position better?
+                    const int c2 = pv[p + 1 - tile_base];
+                    int ml2;
+                    bool un2;
+                    lane_extend(w32, p + 1, c2, C.match_end - p - 1, ml2, un2);
+                    if (ml2 > ml) { p++; c = c2; ml = ml2; un = un2; }
+                }
+                int q = p, cc = c;
+                while (q > la && cc > 0 && win[q - 1] == win[cc - 1]) { q--; cc--; ml++; }
+                recs[cnt][lane] = ((uint32_t)(q - cc) << 16) | ((uint32_t)min(ml, 2047) << 5) | (uint32_t)(q - b0);
+                cnt++;
+                last_q = q; last_ml = ml; last_off = q - cc; unfin = un;
+                la = q + ml;
+                const int rel = la - b0;
+                bits = (un || rel >= 32) ? 0u : (bits & (0xFFFFFFFFu << rel));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.bar_empty[slot]);                  // prev[] of this tile is no longer needed
+
+        // ---- long matches: completed by the whole warp, lowest lane first; one that starts inside a completed
+        // match is dropped (the match before it covers its start; only its tail beyond could have been used)
+        {
+            int covered = 0;
+            for (uint32_t todo = __ballot_sync(FULL_MASK, unfin); todo; todo &= todo - 1) {
+                const int l = __ffs(todo) - 1;
+                const int q = __shfl_sync(FULL_MASK, last_q, l), ml = __shfl_sync(FULL_MASK, last_ml, l);
+                const int off = __shfl_sync(FULL_MASK, last_off, l);
+                if (q < covered) {
+                    if (lane == l) {
+                        cnt--;
+                        if (cnt > 0) {
+                            const uint32_t rc = recs[cnt - 1][lane];
+                            last_q = b0 + (int)(rc & 31u); last_ml = (int)((rc >> 5) & 2047u); last_off = (int)(rc >> 16);
+                        }
+                    }
+                    continue;
+                }
+                const int more = warp_count_equal(w32, q + ml, q + ml - off, C.match_end - q - ml, lane);
+                if (lane == l) last_ml = ml + more;
+                covered = q + ml + more;
+            }
+        }
+
+        // ---- (3) resolve against the entry state of the tile
+        mbar_wait(&S.bar_entry[t], 0);
+        const int x_in = S.st_x[t], anchor_in = S.st_anchor[t], out_in = S.st_out[t];
+        const int E = cnt ? last_q + last_ml : 0;
+        const int pm = warp_incl_max(E, lane);
+        int X = __shfl_up_sync(FULL_MASK, pm, 1);
+        if (lane == 0) X = 0;
+        X = max(X, x_in);                                                // matches of this lane may start here
+        bool emits = false;
+        if (cnt) {
+            const int st = max(last_q, X);
+            emits = (E - st >= MINMATCH) && st < C.mf_end;
+        }
+        const int am = warp_incl_max(emits ? E : 0, lane);
+        int A = __shfl_up_sync(FULL_MASK, am, 1);
+        if (lane == 0) A = 0;
+        A = max(A, anchor_in);                                           // literal run of this lane's first sequence starts here
+        int size = 0;
+        if (emits) {
+            int lit_from = A;
+            for (int i = 0; i < cnt; i++) {
+                const uint32_t rc = recs[i][lane];
+                const int q = b0 + (int)(rc & 31u);
+                const int ml = (i == cnt - 1) ? last_ml : (int)((rc >> 5) & 2047u);
+                const int st = max(q, X), len = q + ml - st;
+                if (len < MINMATCH || st >= C.mf_end) continue;
+                size += seq_size(st - lit_from, len);
+                lit_from = st + len;
+            }
+        }
+        const int incl = warp_incl_sum(size, lane);
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        const int x_out = max(x_in, __shfl_sync(FULL_MASK, pm, 31));
+        const int anchor_out = max(anchor_in, __shfl_sync(FULL_MASK, am, 31));
+        const int out_out = out_in + total;
+        const bool failed = (*reinterpret_cast<volatile int*>(&S.fail) != 0) || out_out > cap;
+        if (lane == 0) {
+            S.st_x[t + 1] = x_out; S.st_anchor[t + 1] = anchor_out; S.st_out[t + 1] = out_out;
+            *reinterpret_cast<volatile int*>(&S.latest_x) = x_out;
+            if (failed) *reinterpret_cast<volatile int*>(&S.fail) = 1;
+            mbar_arrive(&S.bar_entry[t + 1]);
+        }
+
+        // ---- (4) emit: into the staging tile when the tile's bytes fit there (then out with 16-byte stores),
+        // straight to global memory otherwise (long literal runs: poorly compressible data)
+        if (!failed && total > 0) {
+            uint8_t* gdst = payload + out_in;
+            const int g0 = (int)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+            const bool staged = g0 + total <= kStage;
+            uint8_t* o = (staged ? stage + g0 : gdst) + (incl - size);
+            int long_from = 0, long_n = 0;
+            uint8_t* long_to = nullptr;
+            if (emits) {
+                int lit_from = A;
+                for (int i = 0; i < cnt; i++) {
+                    const uint32_t rc = recs[i][lane];
+                    const int q = b0 + (int)(rc & 31u);
+                    const int ml = (i == cnt - 1) ? last_ml : (int)((rc >> 5) & 2047u);
+                    const int st = max(q, X), len = q + ml - st;
+                    if (len < MINMATCH || st >= C.mf_end) continue;
+                    const int lit = st - lit_from, mc = len - MINMATCH;
+                    const uint32_t off = rc >> 16;
+                    *o++ = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mc < 15 ? mc : 15));
+                    if (lit >= 15) { put_ext_bytes(o, lit - 15); o += ext_len(lit - 15); }
+                    if (lit >= kLongLit) { long_from = lit_from; long_n = lit; long_to = o; }
+                    else for (int j = 0; j < lit; j++) o[j] = win[lit_from + j];
+                    o += lit;
+                    o[0] = (uint8_t)off; o[1] = (uint8_t)(off >> 8);
+                    o += 2;
+                    if (mc >= 15) { put_ext_bytes(o, mc - 15); o += ext_len(mc - 15); }
+                    lit_from = st + len;
+                }
+            }
+            // long literal runs: only a lane's first sequence can have one
+            for (uint32_t todo = __ballot_sync(FULL_MASK, long_n > 0); todo; todo &= todo - 1) {
+                const int l = __ffs(todo) - 1;
+                const int from = __shfl_sync(FULL_MASK, long_from, l), cnt_l = __shfl_sync(FULL_MASK, long_n, l);
+                uint8_t* to = reinterpret_cast<uint8_t*>(__shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(long_to), l));
+                if (staged) { for (int k = lane; k < cnt_l; k += 32) to[k] = win[from + k]; }
+                else copy_s2g(to, win + from, cnt_l, lane, 32);
+            }
+            __syncwarp();
+            if (staged) {
+                uint8_t* gb = gdst - g0;                                  // 16-byte aligned
+                const int end = g0 + total;
+                for (int c16 = lane * 16; c16 < end; c16 += 512) {
+                    const int lo = max(c16, g0), hi = min(c16 + 16, end);
+                    if (hi - lo == 16) *reinterpret_cast<uint4*>(gb + c16) = *reinterpret_cast<const uint4*>(stage + c16);
+                    else for (int j = lo; j < hi; j++) gb[j] = stage[j];
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) mbar_arrive(&S.bar_done[t]);
+    }
+}
+
+// ---------------------------------------------------------------- hasher / finisher
+
+// `nchunks` chunks of 512 bytes (32 stripes) starting at word pointer wp (+ byte shift sh), read around L1
+__device__ __forceinline__ uint32_t xxh32_consume_global(uint32_t acc, const uint32_t* wp, uint32_t sh, int nchunks, int lane)
+{
+    auto load = [&](int c, uint32_t (&y)[4]) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int idx = c * 128 + r * 32 + lane;
+            uint32_t v = __ldcg(wp + idx);
+            if (sh) v = __funnelshift_r(v, __ldcg(wp + idx + 1), sh);
+            y[r] = v * XP2;
+        }
+    };
+    uint32_t cur[4] = {0, 0, 0, 0};
+    if (nchunks > 0) load(0, cur);
+    for (int c = 0; c < nchunks; c++) {
+        uint32_t nxt[4] = {0, 0, 0, 0};
+        if (c + 1 < nchunks) load(c + 1, nxt);              // in flight while this chunk goes down the chain
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int t = 0; t < 8; t++) acc = rol32(acc + __shfl_sync(FULL_MASK, cur[r], 4 * t + (lane & 3)), 13) * XP1;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) cur[r] = nxt[r];
+    }
+    return acc;
+}
+
+// the rest of a payload of n bytes of which `done` (a multiple of 16) are already in acc: whole stripes, then the tail
+__device__ __forceinline__ uint32_t xxh32_finish_global(uint32_t acc, const uint8_t* p, uint32_t done, uint32_t n, int lane)
+{
+    const uint32_t stripes = (n >> 4) - (done >> 4);
+    for (uint32_t s0 = 0; s0 < stripes; s0 += 8) {
+        // 8 stripes per round: lane l holds word l of the round
+        const uint32_t idx = done + s0 * 16 + (uint32_t)lane * 4;
+        uint32_t v = 0;
+        if (idx + 4 <= (n & ~15u)) {
+            const uint8_t* q = p + idx;
+            v = (uint32_t)__ldcg(q) | ((uint32_t)__ldcg(q + 1) << 8) | ((uint32_t)__ldcg(q + 2) << 16) | ((uint32_t)__ldcg(q + 3) << 24);
+        }
+        v *= XP2;
+        const uint32_t left = min(8u, stripes - s0);
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const uint32_t x = __shfl_sync(FULL_MASK, v, 4 * t + (lane & 3));
+            if ((uint32_t)t < left) acc = rol32(acc + x, 13) * XP1;
+        }
+    }
+    uint32_t h;
+    if (n >= 16) {
+        const uint32_t v0 = __shfl_sync(FULL_MASK, acc, 0), v1 = __shfl_sync(FULL_MASK, acc, 1);
+        const uint32_t v2 = __shfl_sync(FULL_MASK, acc, 2), v3 = __shfl_sync(FULL_MASK, acc, 3);
+        h = rol32(v0, 1) + rol32(v1, 7) + rol32(v2, 12) + rol32(v3, 18);
+    } else {
+        h = XP5;
+    }
+    h += n;
+    uint32_t i = n & ~15u;
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t v = (uint32_t)__ldcg(p + i) | ((uint32_t)__ldcg(p + i + 1) << 8) | ((uint32_t)__ldcg(p + i + 2) << 16) |
+                           ((uint32_t)__ldcg(p + i + 3) << 24);
+        h = rol32(h + v * XP3, 17) * XP4;
+    }
+    for (; i < n; i++) h = rol32(h + (uint32_t)__ldcg(p + i) * XP5, 11) * XP1;
+    h ^= h >> 15; h *= XP2; h ^= h >> 13; h *= XP3; h ^= h >> 16;
+    return h;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kCtaThreads, 2)
+lz4_compress_cta_kernel(EncodeArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    CtaSmem& S = *reinterpret_cast<CtaSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t b = blockIdx.x;
+    const uint8_t* src = a.src_base + a.src_off[b];
+    const int n_in = (int)a.src_len[b];
+    uint8_t* rec = a.rec_base + (uint64_t)b * a.rec_stride;
+    uint8_t* payload = a.raw_blocks ? rec : rec + 4;
+    const int cap = (int)a.dst_cap;
+    // a block this kernel cannot hold is stored / refused (launch_compress never sends one: see kernels.h)
+    const bool oversize = n_in > 65536;
+    const int n = oversize ? 0 : n_in;
+    const int ntiles = n >= MFLIMIT + 1 ? (n - MFLIMIT + 1 + kTile - 1) / kTile : 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    const uint32_t bulk = aligned ? ((uint32_t)n & ~15u) : 0u;
+
+    if (tid == 0) {
+        mbar_init(&S.bar_load, 1);
+        for (int i = 0; i < kRing; i++) { mbar_init(&S.bar_full[i], 1); mbar_init(&S.bar_empty[i], 1); }
+        for (int i = 0; i <= ntiles; i++) mbar_init(&S.bar_entry[i], 1);
+        for (int i = 0; i < ntiles; i++) mbar_init(&S.bar_done[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.st_x[0] = 0; S.st_anchor[0] = 0; S.st_out[0] = 0;
+        S.latest_x = 0; S.fail = 0;
+        if (bulk) {
+            mbar_arrive_expect_tx(&S.bar_load, bulk);
+            tma_load_bulk(S.win, src, bulk, &S.bar_load);                 // the block, once, into shared memory
+        }
+    }
+    {
+        uint4* t4 = reinterpret_cast<uint4*>(S.table);
+        const uint4 fill = make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (int i = tid; i < (int)(sizeof(S.table) / 16); i += kCtaThreads) t4[i] = fill;
+        // what the bulk copy does not bring: the last n & 15 bytes (or everything, from an unaligned source), zero padding
+        if (aligned) {
+            for (int k = (int)bulk + tid; k < n; k += kCtaThreads) S.win[k] = src[k];
+        } else {
+            const int head = min(n, (int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u));
+            for (int k = tid; k < head; k += kCtaThreads) S.win[k] = src[k];
+            const uint4* s16 = reinterpret_cast<const uint4*>(src + head);
+            const int nvec = (n - head) >> 4;
+            for (int k = tid; k < nvec; k += kCtaThreads) {
+                const uint4 v = s16[k];
+                uint8_t* d = S.win + head + 16 * k;                      // shared side is misaligned by `head`
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 16; j++) d[j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+            }
+            for (int k = head + (nvec << 4) + tid; k < n; k += kCtaThreads) S.win[k] = src[k];
+        }
+        for (int k = n + tid; k < n + kWinPad; k += kCtaThreads) S.win[k] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (!bulk) mbar_arrive(&S.bar_load);
+        mbar_arrive(&S.bar_entry[0]);
+    }
+    mbar_wait(&S.bar_load, 0);
+
+    if (warp == 0) {
+        run_indexer(S, n, ntiles, lane);
+    } else if (warp <= kParsers) {
+        run_parser(S, a, payload, n, ntiles, warp - 1, lane);
+    } else if (a.block_checksum && !a.raw_blocks) {
+        // block checksum as the payload appears: whole 512-byte chunks behind the last completed tile
+        const uintptr_t pa = reinterpret_cast<uintptr_t>(payload);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(pa & ~uintptr_t(3));
+        const uint32_t sh = (uint32_t)(pa & 3u) * 8u;
+        uint32_t acc = xxh32_init(lane);
+        int hashed = 0;
+        for (int t = 0; t < ntiles; t++) {
+            mbar_wait(&S.bar_done[t], 0);
+            if (*reinterpret_cast<volatile int*>(&S.fail)) break;
+            const int avail = S.st_out[t + 1];
+            const int nch = (avail - hashed) / kHashChunk;
+            if (nch > 0) {
+                acc = xxh32_consume_global(acc, wp + hashed / 4, sh, nch, lane);
+                hashed += nch * kHashChunk;
+            }
+        }
+        // park the running state for the finish below (same warp)
+        S.hash_acc[lane] = acc;
+        if (lane == 0) S.hash_done = hashed;
+    }
+    __syncthreads();
+
+    // ---- last literals (lz4.c:1302-1329), stored fallback, framing (blk/blk.go:78-106)
+    const int anchor = S.st_anchor[ntiles], out_end = S.st_out[ntiles];
+    const int run = n - anchor;
+    const int run_ext = run >= 15 ? ext_len(run - 15) : 0;
+    int c = out_end + 1 + run_ext + run;
+    const bool fits = !oversize && S.fail == 0 && c <= cap;
+    if (fits) {
+        if (tid == 0) {
+            payload[out_end] = (uint8_t)((run < 15 ? run : 15) << 4);
+            if (run >= 15) put_ext_bytes(payload + out_end + 1, run - 15);
+        }
+        copy_s2g(payload + out_end + 1 + run_ext, S.win + anchor, run, tid, kCtaThreads);
+    } else {
+        c = 0;
+    }
+    if (a.raw_blocks) {
+        if (tid == 0) a.rec_len[b] = (uint32_t)c;          // 0 = does not fit (clz4.go:40-42)
+        return;
+    }
+    uint32_t word = (uint32_t)c;
+    if (c == 0) {                                           // blk/blk.go:78-92: store raw
+        if (oversize) {
+            for (int k = tid; k < n_in; k += kCtaThreads) payload[k] = src[k];
+        } else {
+            copy_s2g(payload, S.win, n, tid, kCtaThreads);
+        }
+        c = n_in;
+        word = (uint32_t)n_in | 0x80000000u;
+    }
+    __syncthreads();                                        // the payload is complete (block-wide visibility)
+    if (warp != kParsers + 1) return;
+    if (lane == 0) store_le32(rec, word);
+    uint32_t total = 4u + (uint32_t)c;
+    if (a.block_checksum) {
+        uint32_t acc = xxh32_init(lane);
+        uint32_t hashed = 0;
+        uint32_t x;
+        if (fits) {
+            acc = S.hash_acc[lane]; hashed = (uint32_t)S.hash_done;
+            const uintptr_t pa = reinterpret_cast<uintptr_t>(payload);
+            const int nch = (int)(((uint32_t)c - hashed) / kHashChunk);
+            acc = xxh32_consume_global(acc, reinterpret_cast<const uint32_t*>(pa & ~uintptr_t(3)) + hashed / 4, (uint32_t)(pa & 3u) * 8u, nch, lane);
+            hashed += (uint32_t)nch * kHashChunk;
+            x = xxh32_finish_global(acc, payload, hashed, (uint32_t)c, lane);
+        } else if (!oversize) {
+            // a stored block is the window itself: hash it where it lies
+            acc = xxh32_consume_words(acc, reinterpret_cast<const uint32_t*>(S.win), (uint32_t)n >> 4, lane);
+            x = xxh32_finish(acc, S.win, (uint32_t)n);
+        } else {
+            const uintptr_t pa = reinterpret_cast<uintptr_t>(payload);
+            const int nch = c / kHashChunk;
+            acc = xxh32_consume_global(acc, reinterpret_cast<const uint32_t*>(pa & ~uintptr_t(3)), (uint32_t)(pa & 3u) * 8u, nch, lane);
+            x = xxh32_finish_global(acc, payload, (uint32_t)nch * kHashChunk, (uint32_t)c, lane);
+        }
+        if (lane == 0) store_le32(payload + c, x);
+        total += 4;
+    }
+    if (lane == 0) a.rec_len[b] = total;
+}
+
+cudaError_t configure_compress_cta()
+{
+    return cudaFuncSetAttribute(lz4_compress_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+}
+
+cudaError_t launch_compress_cta(const EncodeArgs& a, cudaStream_t stream)
+{
+    lz4_compress_cta_kernel<<<a.nblk, kCtaThreads, sizeof(CtaSmem), stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace plz4

@@ -82,6 +82,8 @@ int ensure_configured()
     if (std::find(done.begin(), done.end(), dev) != done.end()) return 0;
     e = configure_compress();
     if (e != cudaSuccess) return fail(PLZ4CU_ERR_CUDA, "configure_compress", e);
+    e = configure_compress_cta();
+    if (e != cudaSuccess) return fail(PLZ4CU_ERR_CUDA, "configure_compress_cta", e);
     e = configure_decompress();
     if (e != cudaSuccess) return fail(PLZ4CU_ERR_CUDA, "configure_decompress", e);
     done.push_back(dev);
@@ -356,6 +358,8 @@ int plz4cu_compress_batch_device(plz4cu_stream_t stream, const void* src_base, c
     a.src_off = src_off; a.src_len = src_len; a.nblk = nblk; a.dst_cap = dst_cap;
     a.block_checksum = block_checksum; a.raw_blocks = raw_blocks;
     a.rec_base = static_cast<uint8_t*>(rec_base); a.rec_stride = rec_stride; a.rec_len = rec_len;
+    // frame path: a block is at most the frame's block size (dst_cap); raw path: only the slot bounds it
+    a.max_src_len = raw_blocks ? rec_stride : dst_cap;
     if (dict && dict->size) { a.dict = dict->d_bytes; a.dict_size = dict->size; a.dict_table = dict->table(compress_hash_bits(dst_cap)); }
     CU(launch_compress(a, static_cast<cudaStream_t>(stream)));
     g_launches++;
@@ -665,6 +669,7 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         a.src_len = reinterpret_cast<const uint32_t*>(L.off.as<uint64_t>() + cnt);
         a.nblk = cnt; a.dst_cap = dst_cap; a.block_checksum = block_checksum; a.raw_blocks = raw_blocks;
         a.rec_base = L.out.as<uint8_t>(); a.rec_stride = stride; a.rec_len = L.res.as<uint32_t>();
+        a.max_src_len = max_len;
         if (dict && dict->size) { a.dict = dict->d_bytes; a.dict_size = dict->size; a.dict_table = dict->table(compress_hash_bits(dst_cap)); }
         CU(launch_compress(a, L.st));
         CU(launch_pack(L.out.as<uint8_t>(), stride, L.res.as<uint32_t>(), cnt, L.packed.as<uint8_t>(), L.poff.as<uint64_t>(), L.st));

@@ -42,8 +42,12 @@ struct EncodeArgs {
     uint8_t* rec_base;
     uint32_t rec_stride;
     uint32_t* rec_len;
+    uint32_t max_src_len;         // upper bound of src_len[] (exact on the host paths); picks the kernel and the fragment count
 };
 cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream);
+// one CTA per block of <= 64 KiB, block staged in shared memory by TMA (compress_cta.cu); no dictionary
+cudaError_t launch_compress_cta(const EncodeArgs& a, cudaStream_t stream);
+cudaError_t configure_compress_cta();
 cudaError_t configure_compress();     // one-time function attributes (opt-in shared memory)
 
 // dictionary table build (hash -> last position) for a given table size, device side
