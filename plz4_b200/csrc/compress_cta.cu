@@ -36,7 +36,8 @@ namespace {
 constexpr int kCtaThreads = 256;
 constexpr int kParsers = 6;                     // warps 1..6
 constexpr int kTile = 1024;                     // positions per tile: 32 lanes x 32 positions
-constexpr int kRing = 8;                        // tiles of prev[] the indexer may run ahead
+constexpr int kRing = 6;                        // tiles of prev[] the indexer may run ahead
+static_assert(kRing >= kParsers, "a parser's next tile must lie at most one ring phase ahead (parity waits)");
 constexpr int kMaxTiles = 64;
 constexpr int kStage = 2048 + 64;               // staging bytes per parser warp
 constexpr int kLaneCap = 64;                    // a lane extends a match this far by itself
@@ -48,7 +49,7 @@ constexpr int kHashChunk = 512;                 // bytes the hasher consumes per
 struct __align__(16) CtaSmem {
     uint8_t win[65536 + kWinPad];               // the block
     uint8_t stage[kParsers][kStage];
-    uint16_t table[4096];
+    int table[4096];                            // hash -> most recent position, -1 = none
     uint16_t prev[kRing][kTile];
     uint32_t recs[kParsers][8][32];             // [record][lane]: offset<<16 | min(len,2047)<<5 | start-b0
     unsigned long long bar_load;
@@ -88,11 +89,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(ok)
-            : "r"(a), "r"(parity)
+            : "r"(a), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) return;
         if (spins == 64) t0 = clock64();
@@ -208,20 +209,15 @@ __device__ __forceinline__ void run_indexer(CtaSmem& S, int n, int ntiles, int l
             const int base = tile_base + g * 32;
             const int p = base + lane;
             const bool valid = p < hash_end;
-            uint32_t h = 0x10000u | (uint32_t)lane;           // lanes past the end never pair up
-            if (valid) h = (ld4(w32, p) * 2654435761u) >> 20;
-            const uint32_t same = __match_any_sync(FULL_MASK, h);
-            const int hi = 31 - __clz(same);
-            uint32_t old = kNone;
-            if (valid && lane == hi) {                        // the group's last occurrence replaces the table entry
-                old = S.table[h];
-                S.table[h] = (uint16_t)p;
-            }
-            old = __shfl_sync(FULL_MASK, old, hi);
-            const uint32_t lower = same & ((1u << lane) - 1u);
-            const uint32_t cand = lower ? (uint32_t)(base + 31 - __clz(lower)) : old;
+            // One shared-memory atomic per group does the whole exchange: positions only grow, so max == "most recent",
+            // and the value it returns is what stood there before this lane's turn — the table entry from earlier groups
+            // or the position of a lower lane of this group with the same hash.  The hardware serialises same-address
+            // lanes in ascending order (tests/test_gpu_compress.py pins the ratio on short-period data, which depends on
+            // it); any other order would still give valid candidates, since one that is not below p is discarded.
+            int old = -1;
+            if (valid) old = atomicMax(&S.table[(ld4(w32, p) * 2654435761u) >> 20], p);
+            const uint32_t cand = (old >= 0 && old < p) ? (uint32_t)old : kNone;
             pv[g * 32 + lane] = valid ? (uint16_t)cand : (uint16_t)kNone;
-            __syncwarp();                                     // the next group reads what this one wrote
         }
         if (lane == 0) mbar_arrive(&S.bar_full[slot]);
     }
@@ -557,7 +553,7 @@ lz4_compress_cta_kernel(EncodeArgs a)
     }
     {
         uint4* t4 = reinterpret_cast<uint4*>(S.table);
-        const uint4 fill = make_uint4(~0u, ~0u, ~0u, ~0u);
+        const uint4 fill = make_uint4(~0u, ~0u, ~0u, ~0u);       // -1 everywhere
         for (int i = tid; i < (int)(sizeof(S.table) / 16); i += kCtaThreads) t4[i] = fill;
         // what the bulk copy does not bring: the last n & 15 bytes (or everything, from an unaligned source), zero padding
         if (aligned) {
