@@ -7,18 +7,21 @@
 //
 // The block is brought into shared memory ONCE by a TMA bulk copy (cp.async.bulk + mbarrier) and every later
 // access — hashing, candidate verification, match extension, literal copies — is a shared-memory access.
-// The CTA is a small dataflow machine of specialised warps, stages joined by mbarriers (parked waits):
-//   * indexer (1 warp): for EVERY position, in order, the most recent earlier position with the same hash
-//     (liblz4's hash4, lz4.c:777-783, 4096 slots): per 32 positions one table read + one table write, same-group
-//     duplicates resolved with match.any.  Output: prev[] for a tile of 1024 positions, into a ring.
-//   * parsers (6 warps, tiles round-robin): (1) verify every candidate of the tile (4 equal bytes) -> one
-//     32-bit map per lane; (2) every LANE parses its own 32 positions serially — greedy with a one-step lazy
-//     check, forward extension in 4-byte steps, backward extension, at most 8 matches — with no knowledge of
-//     its neighbours; matches may run past the lane's end; matches longer than 68 bytes are completed by the
-//     whole warp; (3) resolve: a prefix maximum over the lanes' match ends tells each lane where the parse
-//     of the lanes before it stops, what it must drop or trim, and where its first literal run begins; sizes
-//     are prefix-summed and every lane writes its own sequences into a staging tile; (4) the tile goes out with
-//     16-byte stores.  Entry state (covered-up-to, literal anchor, output offset) passes from tile to tile.
+// The CTA's warps are workers on tiles of 1024 positions (9 workers, tiles round-robin) plus one hasher; what
+// must happen in order passes from tile to tile through mbarriers (parked waits), everything else runs in parallel:
+//   (1) index: for EVERY position the most recent earlier position with the same hash (liblz4's hash4,
+//       lz4.c:777-783, 4096 slots).  The 4-byte values of the tile are read ahead into registers; when the token
+//       arrives the warp issues one shared-memory atomicMax per 32 positions (positions only grow, so max is
+//       "most recent"; the value returned is the table entry from before, or a lower lane of the same group) and
+//       hands the token on.
+//   (2) verify: every candidate is compared with its position (4 equal bytes) -> one 32-bit map per lane.
+//   (3) parse: every LANE parses its own 32 positions serially — greedy with a one-step lazy check, forward
+//       extension in 4-byte steps, backward extension, at most 8 matches — with no knowledge of its neighbours;
+//       matches may run past the lane's end; matches longer than 68 bytes are completed by the whole warp.
+//   (4) resolve, in tile order: a prefix maximum over the lanes' match ends tells each lane where the parse of the
+//       lanes before it stops, what it must drop or trim, and where its first literal run begins; sizes are
+//       prefix-summed.  Entry state (covered-up-to, literal anchor, output offset) passes from tile to tile.
+//   (5) emit: every lane writes its own sequences into a staging tile, which goes out with 16-byte stores.
 //   * hasher (1 warp): block checksum (xxh32.ChecksumZero, xxh32/xxh32zero.go:238-280) over the payload, chunk
 //     by chunk as tiles complete; then last literals (lz4.c:1302-1329), stored fallback, size word, trailer.
 // The parse is not liblz4's (bytes differ, the reference decodes them; size within the tolerance pinned by
@@ -33,27 +36,24 @@ namespace plz4 {
 
 namespace {
 
-constexpr int kCtaThreads = 256;
-constexpr int kParsers = 6;                     // warps 1..6
+constexpr int kCtaThreads = 320;
+constexpr int kWorkers = 9;                     // warps 0..8; warp 9 hashes
 constexpr int kTile = 1024;                     // positions per tile: 32 lanes x 32 positions
-constexpr int kRing = 6;                        // tiles of prev[] the indexer may run ahead
-static_assert(kRing >= kParsers, "a parser's next tile must lie at most one ring phase ahead (parity waits)");
 constexpr int kMaxTiles = 64;
 constexpr int kStage = 2048 + 64;               // staging bytes per parser warp
 constexpr int kLaneCap = 64;                    // a lane extends a match this far by itself
+constexpr int kLazyBelow = 16;                  // the lazy check is made for matches shorter than this
 constexpr int kLongLit = 48;                    // literal runs from this length on are copied by the whole warp
-constexpr uint32_t kNone = 0xFFFFu;
 constexpr int kWinPad = 32;
 constexpr int kHashChunk = 512;                 // bytes the hasher consumes per step (32 stripes)
 
 struct __align__(16) CtaSmem {
     uint8_t win[65536 + kWinPad];               // the block
-    uint8_t stage[kParsers][kStage];
+    uint8_t stage[kWorkers][kStage];            // per worker: prev[] of its tile (u16 x 1024) while parsing, staging tile while emitting
     int table[4096];                            // hash -> most recent position, -1 = none
-    uint16_t prev[kRing][kTile];
-    uint32_t recs[kParsers][8][32];             // [record][lane]: offset<<16 | min(len,2047)<<5 | start-b0
+    uint32_t recs[kWorkers][8][32];             // [record][lane]: offset<<16 | min(len,2047)<<5 | start-b0
     unsigned long long bar_load;
-    unsigned long long bar_full[kRing], bar_empty[kRing];
+    unsigned long long bar_token[kMaxTiles + 1];      // [t]: the table holds every position before tile t
     unsigned long long bar_entry[kMaxTiles + 1];      // [t]: entry state of tile t is published
     unsigned long long bar_done[kMaxTiles];           // [t]: tile t's bytes are in global memory
     int st_x[kMaxTiles + 1], st_anchor[kMaxTiles + 1], st_out[kMaxTiles + 1];
@@ -83,8 +83,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, u
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
 {
     const uint32_t a = smem_addr(bar);
-    long long t0 = 0;
-    for (uint32_t spins = 0;; spins++) {
+    const long long t0 = clock64();
+    for (uint32_t spins = 1;; spins++) {
         uint32_t ok;
         asm volatile(
             "{\n"
@@ -96,8 +96,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
             : "r"(a), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) return;
-        if (spins == 64) t0 = clock64();
-        if (spins > 64 && (spins & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+        if ((spins & 255u) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_bulk(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar)
@@ -193,37 +192,7 @@ __device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint8_t* src, int n
     for (int k = head + (nvec << 4) + tid; k < n; k += nthr) dst[k] = src[k];
 }
 
-// ---------------------------------------------------------------- indexer
-
-__device__ __forceinline__ void run_indexer(CtaSmem& S, int n, int ntiles, int lane)
-{
-    const uint32_t* __restrict__ w32 = reinterpret_cast<const uint32_t*>(S.win);
-    const int hash_end = n - 3;                               // 4 bytes exist at p < hash_end
-    for (int t = 0; t < ntiles; t++) {
-        const int slot = t % kRing;
-        mbar_wait(&S.bar_empty[slot], (((uint32_t)t / kRing) & 1u) ^ 1u);
-        uint16_t* __restrict__ pv = S.prev[slot];
-        const int tile_base = t * kTile;
-#pragma unroll 4
-        for (int g = 0; g < 32; g++) {
-            const int base = tile_base + g * 32;
-            const int p = base + lane;
-            const bool valid = p < hash_end;
-            // One shared-memory atomic per group does the whole exchange: positions only grow, so max == "most recent",
-            // and the value it returns is what stood there before this lane's turn — the table entry from earlier groups
-            // or the position of a lower lane of this group with the same hash.  The hardware serialises same-address
-            // lanes in ascending order (tests/test_gpu_compress.py pins the ratio on short-period data, which depends on
-            // it); any other order would still give valid candidates, since one that is not below p is discarded.
-            int old = -1;
-            if (valid) old = atomicMax(&S.table[(ld4(w32, p) * 2654435761u) >> 20], p);
-            const uint32_t cand = (old >= 0 && old < p) ? (uint32_t)old : kNone;
-            pv[g * 32 + lane] = valid ? (uint16_t)cand : (uint16_t)kNone;
-        }
-        if (lane == 0) mbar_arrive(&S.bar_full[slot]);
-    }
-}
-
-// ---------------------------------------------------------------- parsers
+// ---------------------------------------------------------------- workers
 
 struct TileCtx {
     const uint32_t* w32;
@@ -232,24 +201,36 @@ struct TileCtx {
     int match_end;     // and must end at or before match_end    (last 5 bytes are literals)
 };
 
-// forward extension of a verified candidate: 4 bytes per step, at most kLaneCap bytes beyond the first four
+// forward extension of a verified candidate (its first four bytes are equal): 16 bytes per round — five words of
+// each side in flight at once — at most kLaneCap bytes beyond the first four
 __device__ __forceinline__ void lane_extend(const uint32_t* __restrict__ w32, int p, int c, int lim, int& ml, bool& un)
 {
-    ml = 4;
+    const uint32_t* __restrict__ wa = w32 + ((p + 4) >> 2);
+    const uint32_t* __restrict__ wb = w32 + ((c + 4) >> 2);
+    const uint32_t sa = (uint32_t)(p & 3) * 8u, sb = (uint32_t)(c & 3) * 8u;
+    uint32_t a0 = wa[0], b0 = wb[0];
+    int done = 4;
     un = false;
     for (;;) {
-        if (ml >= lim) { ml = lim; break; }
-        const uint32_t x = ld4(w32, p + ml) ^ ld4(w32, c + ml);
-        if (x) {
-            ml = min(ml + ((__ffs(x) - 1) >> 3), lim);
+        const uint32_t a1 = wa[1], a2 = wa[2], a3 = wa[3], a4 = wa[4];
+        const uint32_t b1 = wb[1], b2 = wb[2], b3 = wb[3], b4 = wb[4];
+        const uint32_t x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+        const uint32_t x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+        const uint32_t x2 = __funnelshift_r(a2, a3, sa) ^ __funnelshift_r(b2, b3, sb);
+        const uint32_t x3 = __funnelshift_r(a3, a4, sa) ^ __funnelshift_r(b3, b4, sb);
+        if (x0 | x1 | x2 | x3) {
+            const uint32_t xs = x0 ? x0 : (x1 ? x1 : (x2 ? x2 : x3));
+            const int skip = x0 ? 0 : (x1 ? 4 : (x2 ? 8 : 12));
+            done += skip + ((__ffs(xs) - 1) >> 3);
             break;
         }
-        ml += 4;
-        if (ml >= 4 + kLaneCap) {
-            if (ml < lim) un = true; else ml = lim;
-            break;
-        }
+        done += 16;
+        if (done >= lim) break;
+        if (done >= 4 + kLaneCap) { un = true; break; }
+        a0 = a4; b0 = b4;
+        wa += 4; wb += 4;
     }
+    ml = min(done, lim);
 }
 
 __device__ __forceinline__ void put_ext_bytes(uint8_t* o, int rest)
@@ -258,7 +239,7 @@ __device__ __forceinline__ void put_ext_bytes(uint8_t* o, int rest)
     *o = (uint8_t)rest;
 }
 
-__device__ __forceinline__ void run_parser(CtaSmem& S, const EncodeArgs& a, uint8_t* payload, int n, int ntiles, int pw, int lane)
+__device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint8_t* payload, int n, int ntiles, int pw, int lane)
 {
     TileCtx C;
     C.w32 = reinterpret_cast<const uint32_t*>(S.win);
@@ -268,26 +249,60 @@ __device__ __forceinline__ void run_parser(CtaSmem& S, const EncodeArgs& a, uint
     const uint32_t* __restrict__ w32 = C.w32;
     const uint8_t* __restrict__ win = C.win;
     const int cap = (int)a.dst_cap;
+    const int hash_end = n - 3;                               // 4 bytes exist at p < hash_end
     uint8_t* stage = S.stage[pw];
+    uint16_t* pv = reinterpret_cast<uint16_t*>(S.stage[pw]);
     uint32_t(*recs)[32] = S.recs[pw];
 
-    for (int t = pw; t < ntiles; t += kParsers) {
-        const int slot = t % kRing;
+    for (int t = pw; t < ntiles; t += kWorkers) {
         const int tile_base = t * kTile;
         const int b0 = tile_base + 32 * lane;
-        mbar_wait(&S.bar_full[slot], ((uint32_t)t / kRing) & 1u);
-        const uint16_t* __restrict__ pv = S.prev[slot];
+
+        // ---- (1) index, two half tiles of 16 groups.  Position tile_base + 32 g + lane: the word index is the same
+        // for four lanes and the byte shift is the lane's own, so the values come in with immediate offsets.  With
+        // the token in hand the warp issues 16 atomics back to back, parks the results as prev[] and goes on.
+        // The hardware serialises same-address lanes of one atomic in ascending order (tests/test_gpu_compress.py
+        // pins the ratio on short-period data, which depends on it); any other order would still give valid
+        // candidates: one that is not below its position is discarded by (2).
+        {
+            const uint32_t* __restrict__ wt = w32 + (tile_base >> 2) + (lane >> 2);
+            const uint32_t lsh = (uint32_t)(lane & 3) * 8u;
+            const int room = hash_end - tile_base - lane;         // group g is hashed iff 32 g < room
+            uint32_t v[16];
+#pragma unroll
+            for (int g = 0; g < 16; g++) v[g] = __funnelshift_r(wt[8 * g], wt[8 * g + 1], lsh);
+            mbar_wait(&S.bar_token[t], 0);
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                int old[16];
+#pragma unroll
+                for (int g = 0; g < 16; g++) {
+                    old[g] = -1;
+                    if (32 * (g + 16 * half) < room) old[g] = atomicMax(&S.table[(v[g] * 2654435761u) >> 20], tile_base + 512 * half + 32 * g + lane);
+                }
+                if (half == 0) {
+#pragma unroll
+                    for (int g = 0; g < 16; g++) v[g] = __funnelshift_r(wt[128 + 8 * g], wt[128 + 8 * g + 1], lsh);
+                }
+#pragma unroll
+                for (int g = 0; g < 16; g++) pv[512 * half + 32 * g + lane] = (uint16_t)old[g];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.bar_token[t + 1]);
+        }
         const int xhint = *reinterpret_cast<volatile int*>(&S.latest_x);   // a lower bound of this tile's entry state
 
-        // ---- (1) verify the tile's candidates: lane g ends up with the map of positions b0 .. b0+31
+        // ---- (2) verify the tile's candidates: lane g ends up with the map of positions b0 .. b0+31
         uint32_t bits = 0;
         if (xhint < tile_base + kTile) {
+            const uint32_t* __restrict__ wt = w32 + (tile_base >> 2) + (lane >> 2);
+            const uint32_t lsh = (uint32_t)(lane & 3) * 8u;
 #pragma unroll 4
             for (int g = 0; g < 32; g++) {
                 const int p = tile_base + g * 32 + lane;
-                const uint32_t c = pv[g * 32 + lane];
+                const int c = (int)pv[g * 32 + lane];
                 bool okb = false;
-                if (c != kNone && p < C.mf_end) okb = ld4(w32, (int)c) == ld4(w32, p);
+                if (c < p && p < C.mf_end) okb = ld4(w32, c) == __funnelshift_r(wt[8 * g], wt[8 * g + 1], lsh);
                 const uint32_t word = __ballot_sync(FULL_MASK, okb);
                 if (lane == g) bits = word;
             }
@@ -306,7 +321,7 @@ __device__ __forceinline__ void run_parser(CtaSmem& S, const EncodeArgs& a, uint
                 int ml;
                 bool un;
                 lane_extend(w32, p, c, C.match_end - p, ml, un);
-                if (!un && r < 31 && ((bits >> (r + 1)) & 1u)) {          // one-step lazy: is the next position better?
+                if (ml < kLazyBelow && r < 31 && ((bits >> (r + 1)) & 1u)) {          // one-step lazy: is the next position better?
                     const int c2 = pv[p + 1 - tile_base];
                     int ml2;
                     bool un2;
@@ -323,8 +338,7 @@ __device__ __forceinline__ void run_parser(CtaSmem& S, const EncodeArgs& a, uint
                 bits = (un || rel >= 32) ? 0u : (bits & (0xFFFFFFFFu << rel));
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.bar_empty[slot]);                  // prev[] of this tile is no longer needed
+        __syncwarp();                                                    // prev[] is dead from here on: its bytes become the staging tile
 
         // ---- long matches: completed by the whole warp, lowest lane first; one that starts inside a completed
         // match is dropped (the match before it covers its start; only its tail beyond could have been used)
@@ -399,10 +413,9 @@ __device__ __forceinline__ void run_parser(CtaSmem& S, const EncodeArgs& a, uint
             uint8_t* gdst = payload + out_in;
             const int g0 = (int)(reinterpret_cast<uintptr_t>(gdst) & 15u);
             const bool staged = g0 + total <= kStage;
-            uint8_t* o = (staged ? stage + g0 : gdst) + (incl - size);
-            int long_from = 0, long_n = 0;
-            uint8_t* long_to = nullptr;
-            if (emits) {
+            int long_from = 0, long_n = 0, long_at = 0;                  // a literal run left to the whole warp: source, length, offset in the tile's bytes
+            auto emit_lane = [&](uint8_t* base) {
+                uint8_t* o = base + (incl - size);
                 int lit_from = A;
                 for (int i = 0; i < cnt; i++) {
                     const uint32_t rc = recs[i][lane];
@@ -414,7 +427,7 @@ __device__ __forceinline__ void run_parser(CtaSmem& S, const EncodeArgs& a, uint
                     const uint32_t off = rc >> 16;
                     *o++ = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mc < 15 ? mc : 15));
                     if (lit >= 15) { put_ext_bytes(o, lit - 15); o += ext_len(lit - 15); }
-                    if (lit >= kLongLit) { long_from = lit_from; long_n = lit; long_to = o; }
+                    if (lit >= kLongLit) { long_from = lit_from; long_n = lit; long_at = (int)(o - base); }
                     else for (int j = 0; j < lit; j++) o[j] = win[lit_from + j];
                     o += lit;
                     o[0] = (uint8_t)off; o[1] = (uint8_t)(off >> 8);
@@ -422,14 +435,17 @@ __device__ __forceinline__ void run_parser(CtaSmem& S, const EncodeArgs& a, uint
                     if (mc >= 15) { put_ext_bytes(o, mc - 15); o += ext_len(mc - 15); }
                     lit_from = st + len;
                 }
+            };
+            if (emits) {
+                if (staged) emit_lane(S.stage[pw] + g0); else emit_lane(gdst);
             }
             // long literal runs: only a lane's first sequence can have one
             for (uint32_t todo = __ballot_sync(FULL_MASK, long_n > 0); todo; todo &= todo - 1) {
                 const int l = __ffs(todo) - 1;
                 const int from = __shfl_sync(FULL_MASK, long_from, l), cnt_l = __shfl_sync(FULL_MASK, long_n, l);
-                uint8_t* to = reinterpret_cast<uint8_t*>(__shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(long_to), l));
-                if (staged) { for (int k = lane; k < cnt_l; k += 32) to[k] = win[from + k]; }
-                else copy_s2g(to, win + from, cnt_l, lane, 32);
+                const int at = __shfl_sync(FULL_MASK, long_at, l);
+                if (staged) { for (int k = lane; k < cnt_l; k += 32) S.stage[pw][g0 + at + k] = win[from + k]; }
+                else copy_s2g(gdst + at, win + from, cnt_l, lane, 32);
             }
             __syncwarp();
             if (staged) {
@@ -540,7 +556,7 @@ lz4_compress_cta_kernel(EncodeArgs a)
 
     if (tid == 0) {
         mbar_init(&S.bar_load, 1);
-        for (int i = 0; i < kRing; i++) { mbar_init(&S.bar_full[i], 1); mbar_init(&S.bar_empty[i], 1); }
+        for (int i = 0; i <= ntiles; i++) mbar_init(&S.bar_token[i], 1);
         for (int i = 0; i <= ntiles; i++) mbar_init(&S.bar_entry[i], 1);
         for (int i = 0; i < ntiles; i++) mbar_init(&S.bar_done[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -578,13 +594,12 @@ lz4_compress_cta_kernel(EncodeArgs a)
     if (tid == 0) {
         if (!bulk) mbar_arrive(&S.bar_load);
         mbar_arrive(&S.bar_entry[0]);
+        mbar_arrive(&S.bar_token[0]);
     }
     mbar_wait(&S.bar_load, 0);
 
-    if (warp == 0) {
-        run_indexer(S, n, ntiles, lane);
-    } else if (warp <= kParsers) {
-        run_parser(S, a, payload, n, ntiles, warp - 1, lane);
+    if (warp < kWorkers) {
+        run_worker(S, a, payload, n, ntiles, warp, lane);
     } else if (a.block_checksum && !a.raw_blocks) {
         // block checksum as the payload appears: whole 512-byte chunks behind the last completed tile
         const uintptr_t pa = reinterpret_cast<uintptr_t>(payload);
@@ -638,7 +653,7 @@ lz4_compress_cta_kernel(EncodeArgs a)
         word = (uint32_t)n_in | 0x80000000u;
     }
     __syncthreads();                                        // the payload is complete (block-wide visibility)
-    if (warp != kParsers + 1) return;
+    if (warp != kWorkers) return;
     if (lane == 0) store_le32(rec, word);
     uint32_t total = 4u + (uint32_t)c;
     if (a.block_checksum) {
