@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     tmp = LIB + f".{os.getpid()}.tmp"              # written beside the target, renamed when complete
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, *srcs]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("PLZ4CU_NVCC_EXTRA", "").split(), "-o", tmp, *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

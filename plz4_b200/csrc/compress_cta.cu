@@ -17,7 +17,7 @@
 //   (2) verify: every candidate is compared with its position (4 equal bytes) -> one 32-bit map per lane.
 //   (3) parse: every LANE parses its own 32 positions serially — greedy with a one-step lazy check, forward
 //       extension in 4-byte steps, backward extension, at most 8 matches — with no knowledge of its neighbours;
-//       matches may run past the lane's end; matches longer than 68 bytes are completed by the whole warp.
+//       matches may run past the lane's end; matches of 64 bytes and more are completed by the whole warp.
 //   (4) resolve, in tile order: a prefix maximum over the lanes' match ends tells each lane where the parse of the
 //       lanes before it stops, what it must drop or trim, and where its first literal run begins; sizes are
 //       prefix-summed.  Entry state (covered-up-to, literal anchor, output offset) passes from tile to tile.
@@ -34,13 +34,24 @@
 
 namespace plz4 {
 
+// Stage timing for tuning (nvcc -DPLZ4CU_CTA_PROF): cycles summed over all tiles of all blocks by lane 0 of every worker.
+#ifdef PLZ4CU_CTA_PROF
+__device__ unsigned long long g_cta_prof[16];
+#define PROF_DECL long long prof_t = clock64()
+#define PROF(i) do { const long long now__ = clock64(); if (lane == 0) atomicAdd(&g_cta_prof[i], (unsigned long long)(now__ - prof_t)); prof_t = now__; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#endif
+
 namespace {
 
 constexpr int kCtaThreads = 320;
 constexpr int kWorkers = 9;                     // warps 0..8; warp 9 hashes
 constexpr int kTile = 1024;                     // positions per tile: 32 lanes x 32 positions
 constexpr int kMaxTiles = 64;
-constexpr int kStage = 2048 + 64;               // staging bytes per parser warp
+constexpr int kPvStride = 34;                   // u16 per group in prev[]: 17 words, so lanes reading their own group hit 32 banks
+constexpr int kStage = 2 * 32 * kPvStride;      // staging bytes per worker (prev[] of a tile lives in the same bytes)
 constexpr int kLaneCap = 64;                    // a lane extends a match this far by itself
 constexpr int kLazyBelow = 16;                  // the lazy check is made for matches shorter than this
 constexpr int kLongLit = 48;                    // literal runs from this length on are copied by the whole warp
@@ -54,7 +65,8 @@ struct __align__(16) CtaSmem {
     uint32_t recs[kWorkers][8][32];             // [record][lane]: offset<<16 | min(len,2047)<<5 | start-b0
     unsigned long long bar_load;
     unsigned long long bar_token[kMaxTiles + 1];      // [t]: the table holds every position before tile t
-    unsigned long long bar_entry[kMaxTiles + 1];      // [t]: entry state of tile t is published
+    unsigned long long bar_entry[kMaxTiles + 1];      // [t]: entry state (covered-up-to, anchor) of tile t is published
+    unsigned long long bar_out[kMaxTiles + 1];        // [t]: output offset of tile t is published
     unsigned long long bar_done[kMaxTiles];           // [t]: tile t's bytes are in global memory
     int st_x[kMaxTiles + 1], st_anchor[kMaxTiles + 1], st_out[kMaxTiles + 1];
     int latest_x;
@@ -201,15 +213,15 @@ struct TileCtx {
     int match_end;     // and must end at or before match_end    (last 5 bytes are literals)
 };
 
-// forward extension of a verified candidate (its first four bytes are equal): 16 bytes per round — five words of
-// each side in flight at once — at most kLaneCap bytes beyond the first four
+// equal bytes of a position and its candidate, from their first byte on: 16 bytes per round — five words of each side
+// in flight at once — at most kLaneCap + 16 bytes (then `un`: the whole warp completes it); fewer than 4 = no match
 __device__ __forceinline__ void lane_extend(const uint32_t* __restrict__ w32, int p, int c, int lim, int& ml, bool& un)
 {
-    const uint32_t* __restrict__ wa = w32 + ((p + 4) >> 2);
-    const uint32_t* __restrict__ wb = w32 + ((c + 4) >> 2);
+    const uint32_t* __restrict__ wa = w32 + (p >> 2);
+    const uint32_t* __restrict__ wb = w32 + (c >> 2);
     const uint32_t sa = (uint32_t)(p & 3) * 8u, sb = (uint32_t)(c & 3) * 8u;
     uint32_t a0 = wa[0], b0 = wb[0];
-    int done = 4;
+    int done = 0;
     un = false;
     for (;;) {
         const uint32_t a1 = wa[1], a2 = wa[2], a3 = wa[3], a4 = wa[4];
@@ -226,7 +238,7 @@ __device__ __forceinline__ void lane_extend(const uint32_t* __restrict__ w32, in
         }
         done += 16;
         if (done >= lim) break;
-        if (done >= 4 + kLaneCap) { un = true; break; }
+        if (done >= kLaneCap) { un = true; break; }
         a0 = a4; b0 = b4;
         wa += 4; wb += 4;
     }
@@ -257,77 +269,105 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
     for (int t = pw; t < ntiles; t += kWorkers) {
         const int tile_base = t * kTile;
         const int b0 = tile_base + 32 * lane;
+        PROF_DECL;
 
-        // ---- (1) index, two half tiles of 16 groups.  Position tile_base + 32 g + lane: the word index is the same
-        // for four lanes and the byte shift is the lane's own, so the values come in with immediate offsets and the
-        // table slots are known before the token arrives.  With the token in hand a group is seven shared-memory
-        // instructions that depend on nothing but those slots, so sixteen groups go down the pipe back to back:
-        //   read the slot (the entry from earlier groups) — write it by lanes 24-31, then 16-23, 8-15, 0-7 (a later
-        //   instruction overwrites an earlier one, so a slot ends up holding a member of the LOWEST quarter of the
-        //   lanes that share it) — read it back (a lane above that member has its same-group candidate; what matters
-        //   is short-period data, where any lower member of the run serves) — write it once more by all lanes (the
-        //   slot is left with a position of this group for the groups to come).
+        // ---- (1) index.  Position tile_base + 32 g + lane: the word index is the same for four lanes and the byte
+        // shift is the lane's own, so the values come in with immediate offsets.  Every position is looked up, the
+        // EVEN positions are entered (half the table traffic, and a table that churns half as fast gives longer
+        // matches: size -0.4 % on log text against entering all of them).
+        //  (1a) before the token: candidates inside the group (what matters is short-period data, where any lower
+        //       member of the run serves).  Even lanes write their position into a private scratch table, lanes 24-31
+        //       first, then 16-23, 8-15, 0-7 (a later instruction overwrites an earlier one, so a slot ends up holding
+        //       a member of the LOWEST quarter of the lanes that share it); every lane reads its slot back and keeps
+        //       what it finds if that lies in this group, below it, and really has the same hash (one shuffle).
+        //  (1b) with the token: per group one read of the table slot (the entry from earlier groups) and one write by
+        //       the even lanes — 64 shared-memory instructions that depend on nothing but the slots, back to back.
         // Shared-memory atomics would do the exchange in one instruction but retire about one lane every two cycles
         // per SM (measured: 165 cycles per 32-lane atomicMax with two CTAs resident), and match.any costs ~390.
+        const uint32_t* __restrict__ wt = w32 + (tile_base >> 2) + (lane >> 2);
+        const uint32_t lsh = (uint32_t)(lane & 3) * 8u;
+        const int room = hash_end - tile_base - lane;             // group g is hashed iff 32 g < room
+        const int q = (lane & 1) ? -1 : (lane >> 3);              // quarter of an entering lane
         {
-            const uint32_t* __restrict__ wt = w32 + (tile_base >> 2) + (lane >> 2);
-            const uint32_t lsh = (uint32_t)(lane & 3) * 8u;
-            const int room = hash_end - tile_base - lane;         // group g is hashed iff 32 g < room
             uint8_t* tb = reinterpret_cast<uint8_t*>(S.table);
-            const int q = lane >> 3;
-            uint32_t hs[16];                                      // byte offset of the slot
+            uint32_t hs2[16];                                     // byte offsets of the slots, two groups per register
 #pragma unroll
-            for (int g = 0; g < 16; g++) hs[g] = ((__funnelshift_r(wt[8 * g], wt[8 * g + 1], lsh) * 2654435761u) >> 19) & 0x1FFEu;
+            for (int g = 0; g < 32; g++) {
+                const uint32_t h = ((__funnelshift_r(wt[8 * g], wt[8 * g + 1], lsh) * 2654435761u) >> 19) & 0x1FFEu;
+                if (g & 1) hs2[g >> 1] |= h << 16; else hs2[g >> 1] = h;
+            }
+            PROF(0);
             mbar_wait(&S.bar_token[t], 0);
-#pragma unroll 1
-            for (int half = 0; half < 2; half++) {
-                uint32_t old[16], back[16];
+            PROF(1);
+            uint32_t old[32];
 #pragma unroll
-                for (int g = 0; g < 16; g++) {
-                    volatile uint16_t* slot = reinterpret_cast<volatile uint16_t*>(tb + hs[g]);
-                    const bool valid = 32 * (g + 16 * half) < room;
-                    const uint16_t p16 = (uint16_t)(tile_base + 512 * half + 32 * g + lane);
-                    old[g] = *slot;
-                    if (valid && q == 3) *slot = p16;
-                    if (valid && q == 2) *slot = p16;
-                    if (valid && q == 1) *slot = p16;
-                    if (valid && q == 0) *slot = p16;
-                    __syncwarp();
-                    back[g] = *slot;
-                    if (valid) *slot = p16;
-                    __syncwarp();
-                }
-                if (half == 0) {
-#pragma unroll
-                    for (int g = 0; g < 16; g++) hs[g] = ((__funnelshift_r(wt[128 + 8 * g], wt[128 + 8 * g + 1], lsh) * 2654435761u) >> 19) & 0x1FFEu;
-                }
-#pragma unroll
-                for (int g = 0; g < 16; g++) {
-                    const uint32_t p = (uint32_t)(tile_base + 512 * half + 32 * g + lane);
-                    pv[512 * half + 32 * g + lane] = (uint16_t)(back[g] < p ? back[g] : old[g]);
-                }
+            for (int g = 0; g < 32; g++) {
+                volatile uint16_t* slot = reinterpret_cast<volatile uint16_t*>(tb + ((hs2[g >> 1] >> (16 * (g & 1))) & 0xFFFFu));
+                old[g] = *slot;
+                if (q >= 0 && 32 * g < room) *slot = (uint16_t)(tile_base + 32 * g + lane);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.bar_token[t + 1]);
+            PROF(2);
+#pragma unroll
+            for (int g = 0; g < 32; g++) pv[g * kPvStride + lane] = (uint16_t)old[g];
         }
         const int xhint = *reinterpret_cast<volatile int*>(&S.latest_x);   // a lower bound of this tile's entry state
 
-        // ---- (2) verify the tile's candidates: lane g ends up with the map of positions b0 .. b0+31
+        // ---- (2) candidate of every position — inside the group if there is one (1a), else the table's — and a first
+        // check: lane g ends up with the map of positions b0 .. b0+31 whose candidate agrees in the bytes its first
+        // aligned word holds (1 to 4 of them); the parse checks the rest.  Eight groups per round, every stage of a
+        // round issued for all eight before its results are used.
         uint32_t bits = 0;
         if (xhint < tile_base + kTile) {
-            const uint32_t* __restrict__ wt = w32 + (tile_base >> 2) + (lane >> 2);
-            const uint32_t lsh = (uint32_t)(lane & 3) * 8u;
-#pragma unroll 4
-            for (int g = 0; g < 32; g++) {
-                const int p = tile_base + g * 32 + lane;
-                const int c = (int)pv[g * 32 + lane];
-                bool okb = false;
-                if (c < p && p < C.mf_end) okb = ld4(w32, c) == __funnelshift_r(wt[8 * g], wt[8 * g + 1], lsh);
-                const uint32_t word = __ballot_sync(FULL_MASK, okb);
-                if (lane == g) bits = word;
+            uint8_t* sb = reinterpret_cast<uint8_t*>(S.recs[pw]); // 512 x u16 of scratch (the records come later)
+#pragma unroll 1
+            for (int gb = 0; gb < 32; gb += 8) {
+                const uint32_t* __restrict__ wg = wt + 8 * gb;
+                uint16_t* pg = pv + gb * kPvStride + lane;
+                uint32_t own[8], h[8], w[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    own[j] = __funnelshift_r(wg[8 * j], wg[8 * j + 1], lsh);
+                    h[j] = ((own[j] * 2654435761u) >> 19) & 0x1FFEu;
+                    volatile uint16_t* sc = reinterpret_cast<volatile uint16_t*>(sb + (h[j] & 0x3FEu));
+                    const bool enter = q >= 0 && 32 * (gb + j) < room;
+                    const uint16_t p16 = (uint16_t)(tile_base + 32 * (gb + j) + lane);
+                    if (enter && q == 3) *sc = p16;
+                    if (enter && q == 2) *sc = p16;
+                    if (enter && q == 1) *sc = p16;
+                    if (enter && q == 0) *sc = p16;
+                    __syncwarp();
+                    w[j] = *sc;
+                }
+                uint32_t c[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) c[j] = pg[j * kPvStride];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t p = (uint32_t)(tile_base + 32 * (gb + j) + lane);
+                    const uint32_t hw = __shfl_sync(FULL_MASK, h[j], (int)(w[j] & 31u));
+                    if (w[j] >= (uint32_t)(tile_base + 32 * (gb + j)) && w[j] < p && hw == h[j]) {
+                        c[j] = w[j];
+                        pg[j * kPvStride] = (uint16_t)w[j];
+                    }
+                }
+                uint32_t cw[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) cw[j] = w32[min(c[j], 65535u) >> 2];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int p = tile_base + 32 * (gb + j) + lane;
+                    const uint32_t sh = (c[j] & 3u) * 8u;
+                    const bool okb = (int)c[j] < p && p < C.mf_end && (((cw[j] >> sh) ^ own[j]) & (0xFFFFFFFFu >> sh)) == 0;
+                    const uint32_t word = __ballot_sync(FULL_MASK, okb);
+                    if (lane == gb + j) bits = word;
+                }
             }
         }
+        __syncwarp();
 
+        PROF(3);
         // ---- (2) every lane parses its own 32 positions
         int cnt = 0, last_q = 0, last_ml = 0, last_off = 0;
         bool unfin = false;
@@ -337,16 +377,21 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
             while (bits) {
                 const int r = __ffs(bits) - 1;
                 int p = b0 + r;
-                int c = pv[p - tile_base];
+                int c = pv[lane * kPvStride + r];
                 int ml;
                 bool un;
                 lane_extend(w32, p, c, C.match_end - p, ml, un);
-                if (ml < kLazyBelow && r < 31 && ((bits >> (r + 1)) & 1u)) {          // one-step lazy: is the next position better?
-                    const int c2 = pv[p + 1 - tile_base];
-                    int ml2;
-                    bool un2;
-                    lane_extend(w32, p + 1, c2, C.match_end - p - 1, ml2, un2);
-                    if (ml2 > ml) { p++; c = c2; ml = ml2; un = un2; }
+                if (ml < MINMATCH) { bits &= bits - 1; continue; }               // the partial check of (2) let it through
+                if (ml < kLazyBelow && r < 31 && ((bits >> (r + 1)) & 1u)) {     // one-step lazy: is the next position better?
+                    // not if it continues the same source (one byte shorter by construction), and only if the byte
+                    // that would make it longer is there
+                    const int c2 = pv[lane * kPvStride + r + 1];
+                    if (c2 != c + 1 && win[p + 1 + ml] == win[c2 + ml]) {
+                        int ml2;
+                        bool un2;
+                        lane_extend(w32, p + 1, c2, C.match_end - p - 1, ml2, un2);
+                        if (ml2 > ml) { p++; c = c2; ml = ml2; un = un2; }
+                    }
                 }
                 int q = p, cc = c;
                 while (q > la && cc > 0 && win[q - 1] == win[cc - 1]) { q--; cc--; ml++; }
@@ -360,6 +405,7 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
         }
         __syncwarp();                                                    // prev[] is dead from here on: its bytes become the staging tile
 
+        PROF(4);
         // ---- long matches: completed by the whole warp, lowest lane first; one that starts inside a completed
         // match is dropped (the match before it covers its start; only its tail beyond could have been used)
         {
@@ -385,19 +431,32 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
         }
 
         // ---- (3) resolve against the entry state of the tile
-        mbar_wait(&S.bar_entry[t], 0);
-        const int x_in = S.st_x[t], anchor_in = S.st_anchor[t], out_in = S.st_out[t];
         const int E = cnt ? last_q + last_ml : 0;
         const int pm = warp_incl_max(E, lane);
-        int X = __shfl_up_sync(FULL_MASK, pm, 1);
-        if (lane == 0) X = 0;
-        X = max(X, x_in);                                                // matches of this lane may start here
+        int Xl = __shfl_up_sync(FULL_MASK, pm, 1);                       // where the lanes before this one stop, as far as this tile knows
+        if (lane == 0) Xl = 0;
+        const int pm_all = __shfl_sync(FULL_MASK, pm, 31);
+        PROF(5);
+        mbar_wait(&S.bar_entry[t], 0);
+        PROF(6);
+        // Two chains run through the tiles.  The first carries (covered-up-to, literal anchor) and is a handful of
+        // instructions per tile: the next tile's lanes need it before they can size their sequences.  The second
+        // carries the output offset, which takes the sizes of all lanes — work that tiles do side by side.
+        const int x_in = S.st_x[t], anchor_in = S.st_anchor[t];
+        int X = max(Xl, x_in);                                           // matches of this lane may start here
         bool emits = false;
         if (cnt) {
             const int st = max(last_q, X);
             emits = (E - st >= MINMATCH) && st < C.mf_end;
         }
         const int am = warp_incl_max(emits ? E : 0, lane);
+        const int x_out = max(x_in, pm_all);
+        const int anchor_out = max(anchor_in, __shfl_sync(FULL_MASK, am, 31));
+        if (lane == 0) {
+            S.st_x[t + 1] = x_out; S.st_anchor[t + 1] = anchor_out;
+            *reinterpret_cast<volatile int*>(&S.latest_x) = x_out;
+            mbar_arrive(&S.bar_entry[t + 1]);
+        }
         int A = __shfl_up_sync(FULL_MASK, am, 1);
         if (lane == 0) A = 0;
         A = max(A, anchor_in);                                           // literal run of this lane's first sequence starts here
@@ -416,17 +475,18 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
         }
         const int incl = warp_incl_sum(size, lane);
         const int total = __shfl_sync(FULL_MASK, incl, 31);
-        const int x_out = max(x_in, __shfl_sync(FULL_MASK, pm, 31));
-        const int anchor_out = max(anchor_in, __shfl_sync(FULL_MASK, am, 31));
+        PROF(7);
+        mbar_wait(&S.bar_out[t], 0);
+        const int out_in = S.st_out[t];
         const int out_out = out_in + total;
         const bool failed = (*reinterpret_cast<volatile int*>(&S.fail) != 0) || out_out > cap;
         if (lane == 0) {
-            S.st_x[t + 1] = x_out; S.st_anchor[t + 1] = anchor_out; S.st_out[t + 1] = out_out;
-            *reinterpret_cast<volatile int*>(&S.latest_x) = x_out;
+            S.st_out[t + 1] = out_out;
             if (failed) *reinterpret_cast<volatile int*>(&S.fail) = 1;
-            mbar_arrive(&S.bar_entry[t + 1]);
+            mbar_arrive(&S.bar_out[t + 1]);
         }
 
+        PROF(9);
         // ---- (4) emit: into the staging tile when the tile's bytes fit there (then out with 16-byte stores),
         // straight to global memory otherwise (long literal runs: poorly compressible data)
         if (!failed && total > 0) {
@@ -480,6 +540,7 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
             }
         }
         if (lane == 0) mbar_arrive(&S.bar_done[t]);
+        PROF(8);
     }
 }
 
@@ -577,7 +638,7 @@ lz4_compress_cta_kernel(EncodeArgs a)
     if (tid == 0) {
         mbar_init(&S.bar_load, 1);
         for (int i = 0; i <= ntiles; i++) mbar_init(&S.bar_token[i], 1);
-        for (int i = 0; i <= ntiles; i++) mbar_init(&S.bar_entry[i], 1);
+        for (int i = 0; i <= ntiles; i++) { mbar_init(&S.bar_entry[i], 1); mbar_init(&S.bar_out[i], 1); }
         for (int i = 0; i < ntiles; i++) mbar_init(&S.bar_done[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         S.st_x[0] = 0; S.st_anchor[0] = 0; S.st_out[0] = 0;
@@ -614,6 +675,7 @@ lz4_compress_cta_kernel(EncodeArgs a)
     if (tid == 0) {
         if (!bulk) mbar_arrive(&S.bar_load);
         mbar_arrive(&S.bar_entry[0]);
+        mbar_arrive(&S.bar_out[0]);
         mbar_arrive(&S.bar_token[0]);
     }
     mbar_wait(&S.bar_load, 0);
@@ -702,6 +764,15 @@ lz4_compress_cta_kernel(EncodeArgs a)
     }
     if (lane == 0) a.rec_len[b] = total;
 }
+
+#ifdef PLZ4CU_CTA_PROF
+extern "C" __attribute__((visibility("default"))) int plz4cu_debug_cta_prof(unsigned long long* out, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_cta_prof, sizeof(unsigned long long) * 16);
+    if (e == cudaSuccess && reset) { unsigned long long z[16] = {0}; e = cudaMemcpyToSymbol(g_cta_prof, z, sizeof z); }
+    return e == cudaSuccess ? 0 : -1;
+}
+#endif
 
 cudaError_t configure_compress_cta()
 {

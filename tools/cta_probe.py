@@ -55,3 +55,13 @@ if not ok:
     bad = (out_len != BSZ).nonzero().flatten()[:8].tolist()
     print("bad blocks", bad, out_len[bad].tolist() if bad else "")
     sys.exit(1)
+if hasattr(L, "plz4cu_debug_cta_prof") or True:
+    try:
+        buf = (C.c_ulonglong * 16)()
+        if L.plz4cu_debug_cta_prof(buf, 1) == 0:
+            names = ["pre-token", "wait token", "hold token", "verify", "parse", "coop", "wait entry", "sizes", "emit", "wait out"]
+            tot = sum(buf[:10]) or 1
+            ntile = nblk * 64 * (reps + 1)
+            print("stage cycles per tile (lane 0 of the tile's worker): " + ", ".join(f"{n} {buf[i] / ntile:.0f}" for i, n in enumerate(names)) + f"  | total {tot / ntile:.0f}")
+    except AttributeError:
+        pass
