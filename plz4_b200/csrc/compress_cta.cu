@@ -69,7 +69,6 @@ struct __align__(16) CtaSmem {
     unsigned long long bar_out[kMaxTiles + 1];        // [t]: output offset of tile t is published
     unsigned long long bar_done[kMaxTiles];           // [t]: tile t's bytes are in global memory
     int st_x[kMaxTiles + 1], st_anchor[kMaxTiles + 1], st_out[kMaxTiles + 1];
-    int latest_x;
     int fail;
     uint32_t hash_acc[32];                            // the hasher's running state, parked for the finish
     int hash_done;
@@ -266,6 +265,7 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
     uint16_t* pv = reinterpret_cast<uint16_t*>(S.stage[pw]);
     uint32_t(*recs)[32] = S.recs[pw];
 
+    int my_x = 0;                                             // covered-up-to at the exit of this worker's previous tile
     for (int t = pw; t < ntiles; t += kWorkers) {
         const int tile_base = t * kTile;
         const int b0 = tile_base + 32 * lane;
@@ -315,7 +315,7 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
 #pragma unroll
             for (int g = 0; g < 32; g++) pv[g * kPvStride + lane] = (uint16_t)old[g];
         }
-        const int xhint = *reinterpret_cast<volatile int*>(&S.latest_x);   // a lower bound of this tile's entry state
+        const int xhint = my_x;          // a lower bound of this tile's entry state that does not depend on timing: this worker's previous tile
 
         // ---- (2) candidate of every position — inside the group if there is one (1a), else the table's — and a first
         // check: lane g ends up with the map of positions b0 .. b0+31 whose candidate agrees in the bytes its first
@@ -451,10 +451,10 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
         }
         const int am = warp_incl_max(emits ? E : 0, lane);
         const int x_out = max(x_in, pm_all);
+        my_x = x_out;
         const int anchor_out = max(anchor_in, __shfl_sync(FULL_MASK, am, 31));
         if (lane == 0) {
             S.st_x[t + 1] = x_out; S.st_anchor[t + 1] = anchor_out;
-            *reinterpret_cast<volatile int*>(&S.latest_x) = x_out;
             mbar_arrive(&S.bar_entry[t + 1]);
         }
         int A = __shfl_up_sync(FULL_MASK, am, 1);
@@ -642,7 +642,7 @@ lz4_compress_cta_kernel(EncodeArgs a)
         for (int i = 0; i < ntiles; i++) mbar_init(&S.bar_done[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         S.st_x[0] = 0; S.st_anchor[0] = 0; S.st_out[0] = 0;
-        S.latest_x = 0; S.fail = 0;
+        S.fail = 0;
         if (bulk) {
             mbar_arrive_expect_tx(&S.bar_load, bulk);
             tma_load_bulk(S.win, src, bulk, &S.bar_load);                 // the block, once, into shared memory

@@ -121,3 +121,19 @@ def test_dictionary_sizes_and_block_api(gpu, codec, dn):
             r, data = cd.decompress(c, len(m))
             assert r == len(m) and data == m, (dn, n, kind)
             assert gpu.decompress_block(c, dst_cap=len(m), dict=gd) == m
+
+
+def test_compress_is_deterministic(gpu):
+    """The same bytes compress to the same bytes whatever the timing between a block's tiles (stream writers rely on it:
+    progress marks of one run address the frame of another, tests/test_gpu_frame_device.py)."""
+    from tests.datagen import logtext
+    bsz = 65536
+    blocks = [logtext(bsz, seed=1000 + i) for i in range(48)] + [make(k, bsz, seed=3) for k in ["words", "runs", "ab", "zeros", "record1025", "random"]] * 4
+    buf, off = b"".join(blocks), np.arange(len(blocks), dtype=np.uint64) * bsz
+    first = None
+    for _ in range(4):
+        packed, poff = gpu.compress_batch(buf, off, [bsz] * len(blocks), bsz, block_checksum=True)
+        got = (packed[: int(poff[-1])].tobytes(), poff.tobytes())
+        if first is None:
+            first = got
+        assert got == first
