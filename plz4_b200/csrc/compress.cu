@@ -42,6 +42,16 @@ __host__ __device__ __forceinline__ uint32_t table_slot(uint32_t v, int bits)
     const uint32_t h = (v * 2654435761u) >> (32 - bits);       // liblz4's hash4 (lz4.c:777-783)
     return bits == 12 ? (h * 7u) >> 3 : h;
 }
+// liblz4's hash5 (lz4.c:785-795): blocks of 64 KiB + 11 bytes and more are hashed on FIVE bytes (lz4.c:1391-1400 picks
+// byU32 there, and LZ4_hashPosition hashes 5 bytes for every table type but byU16 on 64-bit builds).  The top `bits` bits of
+// ((sequence << 24) * 889523592379) are bits [40-bits, 40) of sequence * prime mod 2^40; b4 is the fifth byte.
+__host__ __device__ __forceinline__ uint32_t table_slot5(uint32_t v, uint32_t b4, int bits)
+{
+    const uint64_t lo = (uint64_t)v * 0x1BBCDCBBull;
+    const uint32_t top = ((uint32_t)(lo >> 32) + v * 0xCFu + b4 * 0x1BBCDCBBu) & 0xFFu;
+    const uint32_t h = ((top << (bits - 8)) | ((uint32_t)lo >> (40 - bits))) & ((1u << bits) - 1u);
+    return bits == 12 ? (h * 7u) >> 3 : h;
+}
 __constant__ int g_back_dev = 1;                // tuning knobs (see configure_compress)
 __constant__ int g_jump_dev = 64;
 __constant__ int g_lazy_dev = 1;                // 0 = greedy; k>0 = take p+1 if its match is longer by >= k
@@ -174,7 +184,7 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             constexpr int kPrewarm = 16384;
             for (int q0 = -min(prefix, kPrewarm); q0 < 0; q0 += 32) {
                 const int q = q0 + lane;
-                const uint32_t hv = table_slot(own4(q), kHashBits);
+                const uint32_t hv = table_slot5(own4(q), own4(q + 1) >> 24, kHashBits);     // kFrag: five-byte hash
                 const uint32_t same = __match_any_sync(FULL_MASK, hv);
                 if ((same >> lane) == 1u) table[hv] = (uint16_t)q;
                 __syncwarp();                        // a later group may overwrite the same slot: keep the order
@@ -198,8 +208,13 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             // ---- (a1) hash, table lookup, same-group duplicates, table update
             uint32_t h = 0x80000000u | (uint32_t)lane;
             int cand = -0x40000000;                               // "none": fails the distance test below
+            uint32_t b4 = 0;                                      // fifth byte of the position (large blocks hash five)
+            if (kFrag) {
+                const uint32_t up1 = __shfl_down_sync(FULL_MASK, v_cur, 1), nx0 = __shfl_sync(FULL_MASK, v_nxt, 0);
+                b4 = (lane == 31 ? nx0 : up1) >> 24;
+            }
             if (valid) {
-                h = table_slot(v, kHashBits);
+                h = kFrag ? table_slot5(v, b4, kHashBits) : table_slot(v, kHashBits);
                 const uint32_t c = table[h];
                 const int vp = p + kVirt;
                 int q = (int)(((uint32_t)vp & 0xFFFF0000u) | c);
@@ -209,7 +224,11 @@ __device__ __forceinline__ int encode_block(const uint8_t* __restrict__ src, int
             const uint32_t same = __match_any_sync(FULL_MASK, h);
             const uint32_t lower = same & ((1u << lane) - 1u);
             if (lower) cand = base + 31 - __clz(lower);
-            if (valid && (same >> lane) == 1u) table[h] = (uint16_t)p;   // most recent occurrence wins
+            if (kFrag) {
+                // large blocks enter the even positions only: a table that churns half as fast keeps longer matches
+                const uint32_t writers = same & ((base & 1) ? 0xAAAAAAAAu : 0x55555555u);
+                if (valid && !(p & 1) && (writers >> lane) == 1u) table[h] = (uint16_t)p;
+            } else if (valid && (same >> lane) == 1u) table[h] = (uint16_t)p;   // most recent occurrence wins
             __syncwarp();
 
             // ---- (a2) every lane measures its own candidate: 1 byte backwards, 15 bytes forwards.
@@ -410,7 +429,7 @@ lz4_compress_kernel(EncodeArgs a)
 // warp (matches may reach back into the previous fragment: same block, same window rules), and a stitch pass joins
 // the fragment streams into one LZ4 block: the literals left over at the end of fragment k become part of the first
 // sequence of fragment k+1, so only that sequence's token / length bytes are rewritten; everything else is copied.
-constexpr int kFragBytes = 65536;
+constexpr int kFragBytes = 131072;             // half the boundaries of 64 KiB fragments (a long match ends at every one)
 constexpr int kHashTileWords = 4096;            // 16 KiB tiles of payload staged in shared memory for the block checksum
 
 struct FragArgs {
@@ -680,12 +699,12 @@ cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
 {
     if (a.nblk == 0) return cudaSuccess;
     const uint32_t max_len = a.max_src_len ? a.max_src_len : a.dst_cap;
-    if (a.dict_size == 0 && max_len <= (uint32_t)kFragBytes && g_cta_min > 0 && max_len >= (uint32_t)g_cta_min)
+    if (a.dict_size == 0 && max_len <= 65536u && g_cta_min > 0 && max_len >= (uint32_t)g_cta_min)
         return launch_compress_cta(a, stream);
     // fragments are sized from the data, not from the room: the caller may offer less room than a block is long
     // (plz4_block.go:100-109 WithBlockDst; the block then compresses into it or is refused, lz4.c:1382)
     const uint32_t frags = (max_len + kFragBytes - 1) / kFragBytes;
-    if (max_len > (uint32_t)kFragBytes && a.dict_size == 0 && frags <= (uint32_t)kMaxFrags) {
+    if (max_len > 65536u && a.dict_size == 0 && frags <= (uint32_t)kMaxFrags) {
         // large blocks: fragment-parallel encode + stitch; scratch comes from the stream-ordered allocator
         FragArgs fa{};
         fa.e = a;

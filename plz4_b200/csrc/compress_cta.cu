@@ -546,74 +546,6 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
 
 // ---------------------------------------------------------------- hasher / finisher
 
-// `nchunks` chunks of 512 bytes (32 stripes) starting at word pointer wp (+ byte shift sh), read around L1
-__device__ __forceinline__ uint32_t xxh32_consume_global(uint32_t acc, const uint32_t* wp, uint32_t sh, int nchunks, int lane)
-{
-    auto load = [&](int c, uint32_t (&y)[4]) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int idx = c * 128 + r * 32 + lane;
-            uint32_t v = __ldcg(wp + idx);
-            if (sh) v = __funnelshift_r(v, __ldcg(wp + idx + 1), sh);
-            y[r] = v * XP2;
-        }
-    };
-    uint32_t cur[4] = {0, 0, 0, 0};
-    if (nchunks > 0) load(0, cur);
-    for (int c = 0; c < nchunks; c++) {
-        uint32_t nxt[4] = {0, 0, 0, 0};
-        if (c + 1 < nchunks) load(c + 1, nxt);              // in flight while this chunk goes down the chain
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-#pragma unroll
-            for (int t = 0; t < 8; t++) acc = rol32(acc + __shfl_sync(FULL_MASK, cur[r], 4 * t + (lane & 3)), 13) * XP1;
-        }
-#pragma unroll
-        for (int r = 0; r < 4; r++) cur[r] = nxt[r];
-    }
-    return acc;
-}
-
-// the rest of a payload of n bytes of which `done` (a multiple of 16) are already in acc: whole stripes, then the tail
-__device__ __forceinline__ uint32_t xxh32_finish_global(uint32_t acc, const uint8_t* p, uint32_t done, uint32_t n, int lane)
-{
-    const uint32_t stripes = (n >> 4) - (done >> 4);
-    for (uint32_t s0 = 0; s0 < stripes; s0 += 8) {
-        // 8 stripes per round: lane l holds word l of the round
-        const uint32_t idx = done + s0 * 16 + (uint32_t)lane * 4;
-        uint32_t v = 0;
-        if (idx + 4 <= (n & ~15u)) {
-            const uint8_t* q = p + idx;
-            v = (uint32_t)__ldcg(q) | ((uint32_t)__ldcg(q + 1) << 8) | ((uint32_t)__ldcg(q + 2) << 16) | ((uint32_t)__ldcg(q + 3) << 24);
-        }
-        v *= XP2;
-        const uint32_t left = min(8u, stripes - s0);
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-            const uint32_t x = __shfl_sync(FULL_MASK, v, 4 * t + (lane & 3));
-            if ((uint32_t)t < left) acc = rol32(acc + x, 13) * XP1;
-        }
-    }
-    uint32_t h;
-    if (n >= 16) {
-        const uint32_t v0 = __shfl_sync(FULL_MASK, acc, 0), v1 = __shfl_sync(FULL_MASK, acc, 1);
-        const uint32_t v2 = __shfl_sync(FULL_MASK, acc, 2), v3 = __shfl_sync(FULL_MASK, acc, 3);
-        h = rol32(v0, 1) + rol32(v1, 7) + rol32(v2, 12) + rol32(v3, 18);
-    } else {
-        h = XP5;
-    }
-    h += n;
-    uint32_t i = n & ~15u;
-    for (; i + 4 <= n; i += 4) {
-        const uint32_t v = (uint32_t)__ldcg(p + i) | ((uint32_t)__ldcg(p + i + 1) << 8) | ((uint32_t)__ldcg(p + i + 2) << 16) |
-                           ((uint32_t)__ldcg(p + i + 3) << 24);
-        h = rol32(h + v * XP3, 17) * XP4;
-    }
-    for (; i < n; i++) h = rol32(h + (uint32_t)__ldcg(p + i) * XP5, 11) * XP1;
-    h ^= h >> 15; h *= XP2; h ^= h >> 13; h *= XP3; h ^= h >> 16;
-    return h;
-}
-
 }  // namespace
 
 __global__ void __launch_bounds__(kCtaThreads, 2)

@@ -137,11 +137,31 @@ __device__ __noinline__ int decode_one(const uint8_t* __restrict__ src, int n, u
 // kRing: the last 64 KiB of output are mirrored in a shared-memory ring and match sources are read from there.
 // Used when a launch has too few blocks to hide global-memory latency with other warps (large block sizes):
 // the per-chunk round trip drops from an L2/HBM access to a shared-memory access.
+// Block checksum carried along with the decode: the payload is hashed 512 bytes at a time just ahead of the parse, so a
+// record comes in from DRAM once (the hash leaves its lines in L1 for the parse) instead of once per pass.
+struct HashAlong {
+    bool on;
+    uint32_t acc;
+    int done;                  // payload bytes in acc (a multiple of 512)
+    const uint32_t* wp;        // word-aligned payload
+    uint32_t sh;               // its byte shift, in bits
+};
+
+// hash the whole 512-byte chunks below `upto` (kept out of line: the decode loop has no registers to lend)
+static __device__ __noinline__ void hash_along(HashAlong& H, int upto, int lane)
+{
+    const int nch = ((upto & ~511) - H.done) >> 9;
+    if (nch > 0) {
+        H.acc = xxh32_consume_global<false>(H.acc, H.wp + (H.done >> 2), H.sh, nch, lane);
+        H.done += nch << 9;
+    }
+}
+
 template <bool kDict, bool kRing>
 __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src, int n,
                                                 uint8_t* dst, int cap,
                                                 const uint8_t* __restrict__ dict, int dsz, int lane, uint32_t* bitmap,
-                                                uint8_t* ring)
+                                                uint8_t* ring, HashAlong& H)
 {
     constexpr int kBatchBytes = 1024;               // output bytes one batch may span (32 bitmap words)
     constexpr int kMaxBatchLit = 63;                // longest literal run a batched sequence may carry (6 bits)
@@ -157,6 +177,7 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
     const uint32_t last4 = (d4 + (uint32_t)n - 1u) >> 2;         // last word holding a valid byte
 
     for (;;) {
+        if (H.on && ip + 256 > H.done && H.done + 512 <= n) hash_along(H, min(ip + 1024, n), lane);
         // ---- 1. parse up to 32 shortcut sequences; lane k latches sequence k.
         // The next 128 compressed bytes sit in registers (one word per lane).  Every lane first computes, for
         // each of its own 4 bytes, how long a sequence header starting there would be (token + literals +
@@ -192,10 +213,17 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
             const uint8_t* dl8 = reinterpret_cast<const uint8_t*>(bitmap);
             uint32_t qb = a0 & 3u;
             uint32_t myq = 0;
+            // four steps per round, each taking effect only while the walk is inside the window (no branch per sequence)
+#pragma unroll 1
             while (nseq < 32 && qb <= 128u - 20u) {
-                if (lane == nseq) myq = qb;
-                qb += dl8[qb];
-                nseq++;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool go = qb <= 128u - 20u;
+                    if (go && lane == nseq) myq = qb;
+                    const uint32_t step = go ? dl8[qb] : 0u;
+                    qb += step;
+                    nseq += go ? 1 : 0;
+                }
             }
             __syncwarp();
             // each lane decodes its own header from the window
@@ -347,23 +375,28 @@ lz4_decompress_kernel(DecodeArgs a)
             if (lane == 0) a.out_len[b] = PLZ4CU_E_OVERFLOW_;
             return;
         }
-        if (a.verify_checksum) {                                  // blk/frame.go:114-127
-            uint32_t want = load_le32(payload + csize);
-            uint32_t got = warp_xxh32(payload, csize, lane);
-            if (want != got) {
-                if (lane == 0) a.out_len[b] = PLZ4CU_E_BLOCKHASH_;
-                return;
-            }
-        }
     }
+    const bool hash_on = !a.raw_blocks && a.verify_checksum != 0;    // blk/frame.go:114-127
+    const uintptr_t pa = reinterpret_cast<uintptr_t>(payload);
+    HashAlong H{hash_on && !stored, xxh32_init(lane), 0, reinterpret_cast<const uint32_t*>(pa & ~uintptr_t(3)), (uint32_t)(pa & 3u) * 8u};
 
     int32_t r;
     if (stored) {
+        if (hash_on && load_le32(payload + csize) != warp_xxh32(payload, csize, lane)) {
+            if (lane == 0) a.out_len[b] = PLZ4CU_E_BLOCKHASH_;
+            return;
+        }
         warp_copy(out, payload, csize, lane);
         r = (int32_t)csize;
     } else {
         r = decode_block<kDict, kRing>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane,
-                                       s_bitmap[warp], dyn_smem);
+                                       s_bitmap[warp], dyn_smem, H);
+        if (H.on) {
+            // the rest of the payload, whatever the decoder made of it: a wrong checksum outranks a decode error
+            // (the reference checks it before it decodes, blk/frame.go:114-127)
+            hash_along(H, (int)csize, lane);
+            if (load_le32(payload + csize) != xxh32_finish_global(H.acc, payload, (uint32_t)H.done, csize, lane)) r = PLZ4CU_E_BLOCKHASH_;
+        }
     }
     if (lane == 0) a.out_len[b] = r;
 }
