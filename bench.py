@@ -9,7 +9,7 @@
   value    : uncompressed bytes through both passes / device time  (2*U / (t_c + t_d)), summed over ranks
   e2e      : the same step through the host-buffer C ABI (plz4cu_*_batch_host) with pinned host
              memory, H2D and D2H inside the timed region
-  roofline : the dominant kernel (lz4_compress_kernel): algorithmic bytes U + C' per launch over
+  roofline : the dominant kernel (lz4_compress_cta_kernel): algorithmic bytes U + C' per launch over
              its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline / --impl reference : the reference's own liblz4 (oracle/_ref, compiled from the
              reference's vendored C) driven by a pthread fan-out over blocks on all host cores
@@ -108,7 +108,6 @@ def cpu_reference(sample_bytes: int, steps: int, warmup: int, threads: int | Non
     """The reference's CPU path (oracle/_ref liblz4 when built, else the pinned port) on all host cores."""
     import numpy as np
     from oracle import oracle as O
-    from plz4_b200 import _lib
     O.build()
     port = O.Port()
     drv = C.CDLL(os.path.join(ROOT, "oracle", "cpu_driver.so"))
@@ -116,6 +115,8 @@ def cpu_reference(sample_bytes: int, steps: int, warmup: int, threads: int | Non
     drv.drv_compress_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     drv.drv_decompress_blocks.restype = C.c_int
     drv.drv_decompress_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    drv.drv_gen_logtext.restype = C.c_int
+    drv.drv_gen_logtext.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
     if O.Ref.available():
         ref = O.Ref()
         kind = "reference"
@@ -128,10 +129,17 @@ def cpu_reference(sample_bytes: int, steps: int, warmup: int, threads: int | Non
         dfn = C.cast(port.lib.orc_lz4_decompress_safe, C.c_void_p)
     xfn = C.cast(port.lib.orc_xxh32, C.c_void_p)
     threads = threads or os.cpu_count() or 1
+    # three buffers of the sample's size live on the host: shrink the sample to what the box has to spare, and say so
+    try:
+        with open("/proc/meminfo") as f:
+            avail = next(int(l.split()[1]) for l in f if l.startswith("MemAvailable")) << 10
+        sample_bytes = min(sample_bytes, max(64 << 20, avail // 5))
+    except Exception:
+        pass
     nblk = max(1, sample_bytes // BSZ)
     total = nblk * BSZ
     src = np.empty(total, dtype=np.uint8)
-    _lib.lib().plz4cu_gen_logtext_host(SEED, 0, C.c_void_p(src.ctypes.data), total)   # host-only helper, no GPU
+    drv.drv_gen_logtext(SEED, 0, C.c_void_p(src.ctypes.data), total, threads)   # the workload's generator, built into the oracle driver
     recs = np.empty(nblk * (BSZ + 8), dtype=np.uint8)
     rec_len = np.zeros(nblk, dtype=np.uint32)
     out = np.empty(total, dtype=np.uint8)
@@ -281,9 +289,8 @@ def run_gpu(args) -> None:
     # ---- e2e through the host-buffer C ABI (pinned host memory; H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
-        # three pinned buffers per rank: keep the box-wide total bounded (16 GiB of input across all ranks)
-        e_gib = args.e2e_gib if world <= 2 else min(args.e2e_gib, 16.0 / world)
-        e_bytes = min(nbytes, int(e_gib * (1 << 30)) // BSZ * BSZ)
+        # the same bytes per GPU at every N (three pinned buffers per rank), so that the 1 -> 8 curve is scaling and nothing else
+        e_bytes = min(nbytes, int(args.e2e_gib * (1 << 30)) // BSZ * BSZ)
         e_blk = e_bytes // BSZ
         h_src = torch.empty(e_bytes, dtype=torch.uint8).pin_memory()
         h_src.copy_(src[:e_bytes])
@@ -353,6 +360,26 @@ def run_gpu(args) -> None:
         c_e = sum(int(q["poff"][q["nb"]]) for q in parts)
         e2e = {"t": te, "steps": e_steps, "bytes": e_bytes, "parts": n_parts,
                "h2d": e_bytes + c_e + e_blk * 24, "d2h": c_e + e_bytes + e_blk * 12 + 8}
+        # copy ceiling: the step's H2D and D2H bytes over the same pinned buffers, both directions at once, no kernels
+        d_a, d_b = src[:e_bytes], out[:e_bytes]
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        up_n, dn_n = e2e["h2d"], e2e["d2h"]
+
+        def copy_step():
+            with torch.cuda.stream(s_up):
+                d_a.copy_(h_src, non_blocking=True)                                       # U up (compress input)
+                recs[:c_e].copy_(h_packed[:c_e], non_blocking=True)                      # C' up (decompress input)
+            with torch.cuda.stream(s_dn):
+                h_packed[:c_e].copy_(recs[:c_e], non_blocking=True)                      # C' down (compress output)
+                h_out.copy_(d_b, non_blocking=True)                                       # U down (decompress output)
+            s_up.synchronize(); s_dn.synchronize()
+        copy_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            copy_step()
+        barrier()
+        e2e["t_copy"] = time.perf_counter() - t0
         del h_src, h_packed, h_out
 
     # ---- max over ranks, sum of work
@@ -365,6 +392,7 @@ def run_gpu(args) -> None:
 
     tt_max, tc_max, td_max = allmax(tt), allmax(tc), allmax(td)
     te_max = allmax(e2e["t"]) if e2e else None
+    tcopy_max = allmax(e2e["t_copy"]) if e2e else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -377,13 +405,15 @@ def run_gpu(args) -> None:
             peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     except Exception:
         pass
-    # DRAM traffic per launch comes from an ncu --set full capture of this same workload (never measured in-run)
-    traffic = {}
+    # DRAM traffic per launch comes from an ncu --set full capture of this same workload made in this round
+    # (tools/ncu_traffic.py writes the file and records the commit it measured); never measured in-run
+    traffic, traffic_src = {}, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f)
         if int(t.get("bytes_per_gpu", 0)) == nbytes:
             traffic = {k: v["traffic"] for k, v in t.items() if isinstance(v, dict) and "traffic" in v}
+            traffic_src = "profiles/r02_traffic.json (ncu --set full, commit %s)" % t.get("commit", "?")
     except Exception:
         pass
     K = args.steps
@@ -398,8 +428,8 @@ def run_gpu(args) -> None:
         "compress_gbs": round(world * nbytes * K / tc_max / 1e9, 3),
         "decompress_gbs": round(world * nbytes * K / td_max / 1e9, 3),
         "compressed_ratio": round(csize / nbytes, 5),
-        "roofline": {"bound": "hbm", "kernel": "lz4_compress_kernel", "achieved": round(c_ach, 2), "peak": peaks, "unit": "GB/s",
-                     "frac": round(c_ach / peaks, 5), "traffic": traffic.get("lz4_compress_kernel"), "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "lz4_compress_cta_kernel", "achieved": round(c_ach, 2), "peak": peaks, "unit": "GB/s",
+                     "frac": round(c_ach / peaks, 5), "traffic": traffic.get("lz4_compress_cta_kernel"), "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo, "launch_ms": round(tc / K * 1e3, 3)},
         "roofline_decompress": {"bound": "hbm", "kernel": "lz4_decompress_kernel", "achieved": round(d_ach, 2), "peak": peaks,
                                 "unit": "GB/s", "frac": round(d_ach / peaks, 5), "traffic": traffic.get("lz4_decompress_kernel"),
@@ -410,11 +440,13 @@ def run_gpu(args) -> None:
         line["e2e"] = {"value": round(world * 2 * e2e["bytes"] * e2e["steps"] / te_max / 1e9, 3), "unit": UNIT,
                        "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                        "bytes_per_gpu": int(e2e["bytes"]), "steps": e2e["steps"],
+                       "copy_ceiling": round(world * 2 * e2e["bytes"] * e2e["steps"] / tcopy_max / 1e9, 3),
+                       "copy_ceiling_note": "same H2D + D2H byte counts per step over the same pinned buffers, both directions at once, no kernels; same unit as value",
                        "host_wait": "spin" if os.environ.get("PLZ4CU_SPIN", "0") not in ("", "0") else "blocking",
                        "api": "plz4cu_compress_batch_host + plz4cu_decompress_batch_host, pinned host buffers, %d parts: part k decompresses while part k+1 compresses" % e2e["parts"]}
-    if not args.no_cpu and world == 1:       # reported on rank 0 at N=1 only
+    if not args.no_cpu:                      # rank 0; the full sample at N=1, a quarter of it at N>1 (the other ranks wait)
         try:
-            r = cpu_reference(args.cpu_sample_mib << 20, 3, 1)
+            r = cpu_reference((args.cpu_sample_mib << 20) // (1 if world == 1 else 4), 3, 1)
             line["cpu_baseline"] = {k: (round(r[k], 4) if isinstance(r[k], float) else r[k])
                                     for k in ("value", "unit", "cores", "kind", "sample", "compress_gbs", "decompress_gbs", "ratio")}
         except Exception as e:        # the baseline is a reported number, never a reason to lose the GPU line
@@ -443,8 +475,8 @@ def main():
     ap.add_argument("--impl", default="plz4_b200", choices=["plz4_b200", "reference"])
     ap.add_argument("--gib", type=float, default=8.0, help="uncompressed GiB per GPU (configs[1] = 8)")
     ap.add_argument("--e2e-parts", type=int, default=8, help="parts the e2e step is cut into (decompress of part k overlaps compress of part k+1); 1 = strictly sequential passes")
-    ap.add_argument("--e2e-gib", type=float, default=8.0, help="GiB per GPU pushed through the host-buffer API per step")
-    ap.add_argument("--cpu-sample-mib", type=int, default=2048, help="bounded sample for the CPU baseline / reference arm")
+    ap.add_argument("--e2e-gib", type=float, default=4.0, help="GiB per GPU pushed through the host-buffer API per step (the same at every N)")
+    ap.add_argument("--cpu-sample-mib", type=int, default=8192, help="sample for the CPU baseline / reference arm (8192 = the whole configs[1] workload)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -172,3 +172,37 @@ DRV_API int drv_compress_dict_msgs(void* reset_fast, void* attach, void* cont, c
     for (i = 1; i < nthreads; i++) pthread_join(th[i], NULL);
     return 0;
 }
+
+/* ---- benchmark input on the host without touching the product library: the workload's definition header
+ * (plz4_b200/csrc/logtext.h, plain C) compiled here, one worker per run of segments. */
+#include "../plz4_b200/csrc/logtext.h"
+
+typedef struct { uint32_t seed; uint64_t first_seg; uint8_t* dst; uint64_t n; uint64_t nseg; atomic_ullong next; } gen_t;
+
+static void* gen_worker(void* arg)
+{
+    gen_t* g = (gen_t*)arg;
+    for (;;) {
+        uint64_t s = atomic_fetch_add(&g->next, 16);
+        if (s >= g->nseg) break;
+        for (uint64_t k = s; k < s + 16 && k < g->nseg; k++) {
+            uint64_t pos = k * LOGTEXT_SEG;
+            uint32_t len = (g->n - pos < LOGTEXT_SEG) ? (uint32_t)(g->n - pos) : LOGTEXT_SEG;
+            lt_fill_segment(g->seed, g->first_seg + k, g->dst + pos, len);
+        }
+    }
+    return 0;
+}
+
+DRV_API int drv_gen_logtext(uint32_t seed, uint64_t first_seg, uint8_t* dst, uint64_t n, int threads)
+{
+    gen_t g;
+    pthread_t th[256];
+    g.seed = seed; g.first_seg = first_seg; g.dst = dst; g.n = n; g.nseg = (n + LOGTEXT_SEG - 1) / LOGTEXT_SEG;
+    atomic_init(&g.next, 0);
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    for (int i = 0; i < threads; i++) pthread_create(&th[i], 0, gen_worker, &g);
+    for (int i = 0; i < threads; i++) pthread_join(th[i], 0);
+    return 0;
+}
