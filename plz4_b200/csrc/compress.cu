@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace plz4 {
@@ -437,6 +438,7 @@ struct FragArgs {
     uint8_t* tmp;              // [nblk * frags_per_block] slots of frag_stride bytes
     uint32_t frag_stride;
     uint32_t frags_per_block;
+    uint32_t frag_bytes;       // input bytes per fragment
     int32_t* frag_len;         // encoded bytes before the final literal run; -2 = fragment does not exist
     uint32_t* frag_tail;       // literal bytes left over at the fragment's end
 };
@@ -497,7 +499,7 @@ lz4_stitch_kernel(FragArgs a)
             const uint32_t w = b * a.frags_per_block + (uint32_t)f;
             const int flen = a.frag_len[w];
             if (flen == -2) { for (int g = f + lane; g < F; g += 32) s_out[g] = -1; break; }
-            const int nf = min(kFragBytes, n_blk - pos);
+            const int nf = min((int)a.frag_bytes, n_blk - pos);
             if (flen <= 0) {                                            // no sequence in this fragment: all literals
                 if (lane == 0) s_out[f] = -1;
                 carry += nf; pos += nf;
@@ -625,6 +627,8 @@ cudaError_t launch_dict_build(const uint8_t* dict, uint32_t dict_size, int bits,
     return cudaGetLastError();
 }
 
+static int g_span_want = 0;       // spans per block, 0 = by the number of blocks; PLZ4CU_SPAN_WANT (experiments)
+static int g_spans = 1;           // blocks above 64 KiB: spans of fragments on the CTA encoder (0: one warp per 128 KiB fragment); PLZ4CU_SPANS
 static int g_cta_min = 8192;      // blocks at least this long get a CTA each (compress_cta.cu); PLZ4CU_CTA_MIN, 0 = never
 static int g_hash_bits = 12;     // 7 KiB of table per warp: 28 resident warps per SM against 12 with liblz4's 13 bits;
                                  // the one-step lazy parse more than pays the ratio back (profiles/r01_sweep.txt)
@@ -657,6 +661,8 @@ cudaError_t configure_compress()
         if (v >= 11 && v <= 13) g_hash_bits = v;
     }
     if (const char* e = getenv("PLZ4CU_CTA_MIN")) g_cta_min = atoi(e);
+    if (const char* e = getenv("PLZ4CU_SPANS")) g_spans = atoi(e);
+    if (const char* e = getenv("PLZ4CU_SPAN_WANT")) g_span_want = atoi(e);
     if (const char* e = getenv("PLZ4CU_BACK")) {
         int v = atoi(e);
         cudaError_t err = cudaMemcpyToSymbol(g_back_dev, &v, sizeof v);
@@ -703,12 +709,41 @@ cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
         return launch_compress_cta(a, stream);
     // fragments are sized from the data, not from the room: the caller may offer less room than a block is long
     // (plz4_block.go:100-109 WithBlockDst; the block then compresses into it or is refused, lz4.c:1382)
+    if (max_len > 65536u && a.dict_size == 0 && g_spans) {
+        // large blocks: spans of 64 KiB fragments, one CTA each (compress_cta.cu), then the stitch; a block is cut into
+        // several spans only as far as it takes to give every SM a CTA
+        const uint32_t nfrag = (max_len + 65535u) / 65536u;
+        uint32_t want = std::min<uint32_t>(nfrag, std::max<uint32_t>(1u, (222u + a.nblk - 1) / a.nblk));
+        if (g_span_want > 0) want = std::min<uint32_t>(nfrag, (uint32_t)g_span_want);
+        want = std::min<uint32_t>(want, (uint32_t)kMaxFrags);
+        const uint32_t span_frags = (nfrag + want - 1) / want;
+        FragArgs fa{};
+        fa.e = a;
+        fa.frags_per_block = (nfrag + span_frags - 1) / span_frags;
+        fa.frag_bytes = span_frags * 65536u;
+        fa.frag_stride = (uint32_t)(((uint64_t)fa.frag_bytes + fa.frag_bytes / 255 + 16 + 15) & ~15ull);
+        const uint64_t nspan = (uint64_t)a.nblk * fa.frags_per_block;
+        void* scratch = nullptr;
+        cudaError_t e = cudaMallocAsync(&scratch, nspan * fa.frag_stride + nspan * 8, stream);
+        if (e != cudaSuccess) return e;
+        fa.tmp = static_cast<uint8_t*>(scratch);
+        fa.frag_len = reinterpret_cast<int32_t*>(fa.tmp + nspan * fa.frag_stride);
+        fa.frag_tail = reinterpret_cast<uint32_t*>(fa.frag_len + nspan);
+        e = launch_compress_spans(a, fa.tmp, fa.frag_stride, fa.frags_per_block, fa.frag_bytes, fa.frag_len, fa.frag_tail, stream);
+        if (e == cudaSuccess) {
+            lz4_stitch_kernel<<<a.nblk, kStitchWarps * 32, 0, stream>>>(fa);
+            e = cudaGetLastError();
+        }
+        cudaError_t e2 = cudaFreeAsync(scratch, stream);
+        return e != cudaSuccess ? e : e2;
+    }
     const uint32_t frags = (max_len + kFragBytes - 1) / kFragBytes;
     if (max_len > 65536u && a.dict_size == 0 && frags <= (uint32_t)kMaxFrags) {
-        // large blocks: fragment-parallel encode + stitch; scratch comes from the stream-ordered allocator
+        // (PLZ4CU_SPANS=0) fragment-parallel encode, one warp per 128 KiB fragment, + stitch
         FragArgs fa{};
         fa.e = a;
         fa.frags_per_block = frags;
+        fa.frag_bytes = kFragBytes;
         fa.frag_stride = (uint32_t)((kFragBytes + kFragBytes / 255 + 16 + 15) & ~15);
         const uint64_t nfrag = (uint64_t)a.nblk * fa.frags_per_block;
         void* scratch = nullptr;

@@ -58,11 +58,15 @@ constexpr int kLongLit = 48;                    // literal runs from this length
 constexpr int kWinPad = 32;
 constexpr int kHashChunk = 512;                 // bytes the hasher consumes per step (32 stripes)
 
-struct __align__(16) CtaSmem {
-    uint8_t win[65536 + kWinPad];               // the block
-    uint8_t stage[kWorkers][kStage];            // per worker: prev[] of its tile (u16 x 1024) while parsing, staging tile while emitting
-    uint16_t table[4096];                       // hash -> a recent position, 0xFFFF = none
-    uint32_t recs[kWorkers][8][32];             // [record][lane]: offset<<16 | min(len,2047)<<5 | start-b0
+constexpr int kSpanWorkers = 20;                // large blocks: one CTA per SM, every warp a worker
+constexpr int kSpanThreads = kSpanWorkers * 32;
+
+template <int kWin, int kNW>
+struct __align__(16) CtaSmemT {
+    uint8_t win[kWin + kWinPad];                // the block (large blocks: the fragment before the current one, then the current one)
+    uint8_t stage[kNW][kStage];                 // per worker: prev[] of its tile (u16 x 1024) while parsing, staging tile while emitting
+    uint16_t table[4096];                       // hash -> a recent position (its low 16 bits), 0xFFFF = none
+    uint32_t recs[kNW][8][32];                  // [record][lane]: offset<<16 | min(len,2047)<<5 | start-b0
     unsigned long long bar_load;
     unsigned long long bar_token[kMaxTiles + 1];      // [t]: the table holds every position before tile t
     unsigned long long bar_entry[kMaxTiles + 1];      // [t]: entry state (covered-up-to, anchor) of tile t is published
@@ -72,6 +76,26 @@ struct __align__(16) CtaSmem {
     int fail;
     uint32_t hash_acc[32];                            // the hasher's running state, parked for the finish
     int hash_done;
+};
+using CtaSmem = CtaSmemT<65536, kWorkers>;
+using SpanSmem = CtaSmemT<131072, kSpanWorkers>;
+
+// What a worker needs to know about the stretch of input it works on.  Positions are absolute inside the block; w32 / win
+// are biased so that w32[p >> 2] / win[p] is position p whichever part of the block the shared-memory window holds.
+struct TileEnv {
+    const uint32_t* w32;
+    const uint8_t* win;
+    const uint8_t* gsrc;   // the block in global memory (large blocks: literal runs that reach behind the window)
+    uint8_t* payload;      // where the sequences go
+    int pos0;              // position of tile 0
+    int ntiles;
+    int hash_end;          // positions below it are hashed
+    int mf_end;            // a match may start at p < mf_end        (lz4.c:963: last match starts <= n-12)
+    int match_end;         // and must end at or before match_end    (last 5 bytes are literals)
+    int lo_valid;          // lowest position a candidate may have
+    int cap;
+    uint32_t parity;       // phase of the per-tile barriers (large blocks reuse them fragment after fragment)
+    bool index_only;       // large blocks: the fragment before a span only warms the table
 };
 
 // ---------------------------------------------------------------- mbarrier / TMA plumbing
@@ -205,13 +229,6 @@ __device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint8_t* src, int n
 
 // ---------------------------------------------------------------- workers
 
-struct TileCtx {
-    const uint32_t* w32;
-    const uint8_t* win;
-    int mf_end;        // a match may start at p < mf_end        (lz4.c:963: last match starts <= n-12)
-    int match_end;     // and must end at or before match_end    (last 5 bytes are literals)
-};
-
 // equal bytes of a position and its candidate, from their first byte on: 16 bytes per round — five words of each side
 // in flight at once — at most kLaneCap + 16 bytes (then `un`: the whole warp completes it); fewer than 4 = no match
 __device__ __forceinline__ void lane_extend(const uint32_t* __restrict__ w32, int p, int c, int lim, int& ml, bool& un)
@@ -250,24 +267,44 @@ __device__ __forceinline__ void put_ext_bytes(uint8_t* o, int rest)
     *o = (uint8_t)rest;
 }
 
-__device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint8_t* payload, int n, int ntiles, int pw, int lane)
+// hash of the 4 (blocks up to 64 KiB: liblz4's hash4, lz4.c:777-783) or 5 (larger blocks: its hash5, lz4.c:785-795) bytes at a
+// position, as the byte offset of the table slot; w0, w1 are the aligned words holding them, lsh the position's byte shift
+template <bool kLarge>
+__device__ __forceinline__ uint32_t slot_offset(uint32_t w0, uint32_t w1, uint32_t lsh)
 {
-    TileCtx C;
-    C.w32 = reinterpret_cast<const uint32_t*>(S.win);
-    C.win = S.win;
-    C.mf_end = n - MFLIMIT + 1;
-    C.match_end = n - LASTLITERALS;
+    const uint32_t v = __funnelshift_r(w0, w1, lsh);
+    if (!kLarge) return ((v * 2654435761u) >> 19) & 0x1FFEu;
+    // bits [28, 40) of (five bytes) * 889523592379 mod 2^40
+    const uint32_t b4 = (w1 >> lsh) & 0xFFu;
+    const uint32_t lo = v * 0x1BBCDCBBu, hi = __umulhi(v, 0x1BBCDCBBu);
+    const uint32_t top = (hi + v * 0xCFu + b4 * 0x1BBCDCBBu) & 0xFFu;
+    return (((top << 4) | (lo >> 28)) << 1) & 0x1FFEu;
+}
+
+// candidate position from its 16 stored bits: the one at most 65535 below p (large blocks; small ones store it whole)
+__device__ __forceinline__ int cand_abs(int p, uint32_t c16)
+{
+    int c = (p & ~0xFFFF) | (int)c16;
+    if (c >= p) c -= 65536;
+    return c;
+}
+
+template <bool kLarge, int kNW, typename SM>
+__device__ __forceinline__ void run_worker(SM& S, const TileEnv& C, int pw, int lane, int& my_x)
+{
     const uint32_t* __restrict__ w32 = C.w32;
     const uint8_t* __restrict__ win = C.win;
-    const int cap = (int)a.dst_cap;
-    const int hash_end = n - 3;                               // 4 bytes exist at p < hash_end
+    uint8_t* payload = C.payload;
+    const int cap = C.cap;
+    const int hash_end = C.hash_end;
+    const int ntiles = C.ntiles;
+    const uint32_t par = C.parity;
     uint8_t* stage = S.stage[pw];
     uint16_t* pv = reinterpret_cast<uint16_t*>(S.stage[pw]);
     uint32_t(*recs)[32] = S.recs[pw];
 
-    int my_x = 0;                                             // covered-up-to at the exit of this worker's previous tile
-    for (int t = pw; t < ntiles; t += kWorkers) {
-        const int tile_base = t * kTile;
+    for (int t = pw; t < ntiles; t += kNW) {
+        const int tile_base = C.pos0 + t * kTile;
         const int b0 = tile_base + 32 * lane;
         PROF_DECL;
 
@@ -296,11 +333,11 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
             uint32_t hs2[16];                                     // byte offsets of the slots, two groups per register
 #pragma unroll
             for (int g = 0; g < 32; g++) {
-                const uint32_t h = ((__funnelshift_r(wt[8 * g], wt[8 * g + 1], lsh) * 2654435761u) >> 19) & 0x1FFEu;
+                const uint32_t h = slot_offset<kLarge>(wt[8 * g], wt[8 * g + 1], lsh);
                 if (g & 1) hs2[g >> 1] |= h << 16; else hs2[g >> 1] = h;
             }
             PROF(0);
-            mbar_wait(&S.bar_token[t], 0);
+            mbar_wait(&S.bar_token[t], par);
             PROF(1);
             uint32_t old[32];
 #pragma unroll
@@ -314,6 +351,10 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
             PROF(2);
 #pragma unroll
             for (int g = 0; g < 32; g++) pv[g * kPvStride + lane] = (uint16_t)old[g];
+        }
+        if (kLarge && C.index_only) {                                    // table warmed; keep the other chains' phases in step
+            if (lane == 0) { mbar_arrive(&S.bar_entry[t + 1]); mbar_arrive(&S.bar_out[t + 1]); mbar_arrive(&S.bar_done[t]); }
+            continue;
         }
         const int xhint = my_x;          // a lower bound of this tile's entry state that does not depend on timing: this worker's previous tile
 
@@ -332,7 +373,7 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     own[j] = __funnelshift_r(wg[8 * j], wg[8 * j + 1], lsh);
-                    h[j] = ((own[j] * 2654435761u) >> 19) & 0x1FFEu;
+                    h[j] = slot_offset<kLarge>(wg[8 * j], wg[8 * j + 1], lsh);
                     volatile uint16_t* sc = reinterpret_cast<volatile uint16_t*>(sb + (h[j] & 0x3FEu));
                     const bool enter = q >= 0 && 32 * (gb + j) < room;
                     const uint16_t p16 = (uint16_t)(tile_base + 32 * (gb + j) + lane);
@@ -345,21 +386,34 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
                 for (int j = 0; j < 8; j++) c[j] = pg[j * kPvStride];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const uint32_t p = (uint32_t)(tile_base + 32 * (gb + j) + lane);
+                    // 16-bit arithmetic: a group never straddles a multiple of 65536
+                    const uint32_t g16 = (uint32_t)(tile_base + 32 * (gb + j)) & 0xFFFFu;
                     const uint32_t hw = __shfl_sync(FULL_MASK, h[j], (int)(w[j] & 31u));
-                    if (w[j] >= (uint32_t)(tile_base + 32 * (gb + j)) && w[j] < p && hw == h[j]) {
+                    if (w[j] >= g16 && w[j] < g16 + (uint32_t)lane && hw == h[j]) {
                         c[j] = w[j];
                         pg[j * kPvStride] = (uint16_t)w[j];
                     }
                 }
                 uint32_t cw[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) cw[j] = w32[min(c[j], 65535u) >> 2];
+                int ca[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const int p = tile_base + 32 * (gb + j) + lane;
-                    const uint32_t sh = (c[j] & 3u) * 8u;
-                    const bool okb = (int)c[j] < p && p < C.mf_end && (((cw[j] >> sh) ^ own[j]) & (0xFFFFFFFFu >> sh)) == 0;
+                    if (kLarge) {
+                        ca[j] = cand_abs(p, c[j]);
+                        // none: an empty slot, a position from before the span, or one exactly 65536 back (same low bits: an
+                        // offset LZ4 cannot express)
+                        if (c[j] == 0xFFFFu || ca[j] < C.lo_valid || ca[j] == p - 65536) ca[j] = p;
+                    } else {
+                        ca[j] = (int)c[j] < p ? (int)c[j] : p;
+                    }
+                    cw[j] = w32[ca[j] >> 2];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int p = tile_base + 32 * (gb + j) + lane;
+                    const uint32_t sh = (uint32_t)(ca[j] & 3) * 8u;
+                    const bool okb = ca[j] < p && p < C.mf_end && (((cw[j] >> sh) ^ own[j]) & (0xFFFFFFFFu >> sh)) == 0;
                     const uint32_t word = __ballot_sync(FULL_MASK, okb);
                     if (lane == gb + j) bits = word;
                 }
@@ -377,7 +431,7 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
             while (bits) {
                 const int r = __ffs(bits) - 1;
                 int p = b0 + r;
-                int c = pv[lane * kPvStride + r];
+                int c = kLarge ? cand_abs(p, pv[lane * kPvStride + r]) : (int)pv[lane * kPvStride + r];
                 int ml;
                 bool un;
                 lane_extend(w32, p, c, C.match_end - p, ml, un);
@@ -385,7 +439,7 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
                 if (ml < kLazyBelow && r < 31 && ((bits >> (r + 1)) & 1u)) {     // one-step lazy: is the next position better?
                     // not if it continues the same source (one byte shorter by construction), and only if the byte
                     // that would make it longer is there
-                    const int c2 = pv[lane * kPvStride + r + 1];
+                    const int c2 = kLarge ? cand_abs(p + 1, pv[lane * kPvStride + r + 1]) : (int)pv[lane * kPvStride + r + 1];
                     if (c2 != c + 1 && win[p + 1 + ml] == win[c2 + ml]) {
                         int ml2;
                         bool un2;
@@ -394,7 +448,7 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
                     }
                 }
                 int q = p, cc = c;
-                while (q > la && cc > 0 && win[q - 1] == win[cc - 1]) { q--; cc--; ml++; }
+                while (q > la && cc > C.lo_valid && win[q - 1] == win[cc - 1]) { q--; cc--; ml++; }
                 recs[cnt][lane] = ((uint32_t)(q - cc) << 16) | ((uint32_t)min(ml, 2047) << 5) | (uint32_t)(q - b0);
                 cnt++;
                 last_q = q; last_ml = ml; last_off = q - cc; unfin = un;
@@ -437,7 +491,7 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
         if (lane == 0) Xl = 0;
         const int pm_all = __shfl_sync(FULL_MASK, pm, 31);
         PROF(5);
-        mbar_wait(&S.bar_entry[t], 0);
+        mbar_wait(&S.bar_entry[t], par);
         PROF(6);
         // Two chains run through the tiles.  The first carries (covered-up-to, literal anchor) and is a handful of
         // instructions per tile: the next tile's lanes need it before they can size their sequences.  The second
@@ -476,7 +530,7 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
         const int incl = warp_incl_sum(size, lane);
         const int total = __shfl_sync(FULL_MASK, incl, 31);
         PROF(7);
-        mbar_wait(&S.bar_out[t], 0);
+        mbar_wait(&S.bar_out[t], par);
         const int out_in = S.st_out[t];
         const int out_out = out_in + total;
         const bool failed = (*reinterpret_cast<volatile int*>(&S.fail) != 0) || out_out > cap;
@@ -524,7 +578,9 @@ __device__ __forceinline__ void run_worker(CtaSmem& S, const EncodeArgs& a, uint
                 const int l = __ffs(todo) - 1;
                 const int from = __shfl_sync(FULL_MASK, long_from, l), cnt_l = __shfl_sync(FULL_MASK, long_n, l);
                 const int at = __shfl_sync(FULL_MASK, long_at, l);
-                if (staged) { for (int k = lane; k < cnt_l; k += 32) S.stage[pw][g0 + at + k] = win[from + k]; }
+                // a long run may begin behind the window when blocks are large: those come from global memory
+                if (staged) { for (int k = lane; k < cnt_l; k += 32) S.stage[pw][g0 + at + k] = kLarge ? C.gsrc[from + k] : win[from + k]; }
+                else if (kLarge) warp_copy(gdst + at, C.gsrc + from, (uint32_t)cnt_l, lane);
                 else copy_s2g(gdst + at, win + from, cnt_l, lane, 32);
             }
             __syncwarp();
@@ -613,7 +669,13 @@ lz4_compress_cta_kernel(EncodeArgs a)
     mbar_wait(&S.bar_load, 0);
 
     if (warp < kWorkers) {
-        run_worker(S, a, payload, n, ntiles, warp, lane);
+        TileEnv env;
+        env.w32 = reinterpret_cast<const uint32_t*>(S.win); env.win = S.win; env.gsrc = src; env.payload = payload;
+        env.pos0 = 0; env.ntiles = ntiles;
+        env.hash_end = n - 3; env.mf_end = n - MFLIMIT + 1; env.match_end = n - LASTLITERALS;
+        env.lo_valid = 0; env.cap = cap; env.parity = 0; env.index_only = false;
+        int my_x = 0;                                         // covered-up-to at the exit of this worker's previous tile
+        run_worker<false, kWorkers>(S, env, warp, lane, my_x);
     } else if (a.block_checksum && !a.raw_blocks) {
         // block checksum as the payload appears: whole 512-byte chunks behind the last completed tile
         const uintptr_t pa = reinterpret_cast<uintptr_t>(payload);
@@ -697,18 +759,119 @@ lz4_compress_cta_kernel(EncodeArgs a)
     if (lane == 0) a.rec_len[b] = total;
 }
 
-#ifdef PLZ4CU_CTA_PROF
-extern "C" __attribute__((visibility("default"))) int plz4cu_debug_cta_prof(unsigned long long* out, int reset)
+
+// ---------------------------------------------------------------- blocks larger than 64 KiB
+//
+// One CTA per SPAN: a run of consecutive 64 KiB fragments of one block, encoded one after the other by the same
+// workers with the table kept.  The window holds the fragment before the current one next to it (moved down when
+// the next one is loaded), so a candidate up to 65535 bytes back is always in shared memory and the parse behaves as
+// liblz4's does on a large block — five-byte hash included (lz4.c:785-795,1391-1400).  A match stops at the end of its
+// fragment (the next one is not loaded yet) and goes on as a new sequence with no literals: four or five bytes per
+// 64 KiB on data that is one long match.  A block is cut into several spans only when the launch has fewer blocks than
+// the GPU has SMs; a span that does not begin its block first runs the fragment before it through the index alone, and
+// lz4_stitch_kernel (compress.cu) joins the spans' streams: the literals left at the end of one become part of the
+// first sequence of the next.
+__global__ void __launch_bounds__(kSpanThreads, 1)
+lz4_compress_span_kernel(EncodeArgs a, uint8_t* tmp, uint32_t slot_stride, uint32_t spans_per_block, uint32_t span_bytes,
+                         int32_t* span_len, uint32_t* span_tail)
 {
-    cudaError_t e = cudaMemcpyFromSymbol(out, g_cta_prof, sizeof(unsigned long long) * 16);
-    if (e == cudaSuccess && reset) { unsigned long long z[16] = {0}; e = cudaMemcpyToSymbol(g_cta_prof, z, sizeof z); }
-    return e == cudaSuccess ? 0 : -1;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    SpanSmem& S = *reinterpret_cast<SpanSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t w = blockIdx.x, b = w / spans_per_block, sp = w % spans_per_block;
+    if (b >= a.nblk) return;
+    const uint8_t* src = a.src_base + a.src_off[b];
+    const int n_blk = (int)a.src_len[b];
+    const int span_start = (int)(sp * span_bytes);
+    if (span_start >= n_blk && sp != 0) {
+        if (tid == 0) span_len[w] = -2;                           // this span does not exist
+        return;
+    }
+    const int span_end = min(n_blk, span_start + (int)span_bytes);
+    uint8_t* out = tmp + (uint64_t)w * slot_stride;
+
+    if (tid == 0) {
+        mbar_init(&S.bar_load, 1);
+        for (int i = 0; i <= kMaxTiles; i++) { mbar_init(&S.bar_token[i], 1); mbar_init(&S.bar_entry[i], 1); mbar_init(&S.bar_out[i], 1); }
+        for (int i = 0; i < kMaxTiles; i++) mbar_init(&S.bar_done[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.fail = 0;
+    }
+    {
+        uint4* t4 = reinterpret_cast<uint4*>(S.table);
+        const uint4 fill = make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (int i = tid; i < (int)(sizeof(S.table) / 16); i += kSpanThreads) t4[i] = fill;
+    }
+    uint8_t* cur = S.win + 65536;                                 // the current fragment; the one before it lies below
+    int my_x = span_start;
+    int carry_x = span_start, carry_anchor = span_start, carry_out = 0;
+    uint32_t it = 0;
+    for (int fs = span_start - (sp != 0 ? 65536 : 0); fs < span_end; fs += 65536, it++) {
+        const bool warm = fs < span_start;
+        const int fe = warm ? fs + 65536 : min(fs + 65536, span_end);      // end of the fragment's bytes
+        __syncthreads();                                          // every worker is done with the fragment before
+        if (it > 0) {
+            uint4* d = reinterpret_cast<uint4*>(S.win);
+            const uint4* s4 = reinterpret_cast<const uint4*>(cur);
+            for (int i = tid; i < 4096; i += kSpanThreads) d[i] = s4[i];
+        }
+        __syncthreads();
+        const uint8_t* fsrc = src + fs;
+        const int fn = fe - fs;
+        const bool aligned = (reinterpret_cast<uintptr_t>(fsrc) & 15u) == 0;
+        const uint32_t bulk = aligned ? ((uint32_t)fn & ~15u) : 0u;
+        if (tid == 0 && bulk) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the bulk copy overwrites bytes just read by ordinary loads
+            mbar_arrive_expect_tx(&S.bar_load, bulk);
+            tma_load_bulk(cur, fsrc, bulk, &S.bar_load);
+        }
+        for (int k = (int)bulk + tid; k < fn; k += kSpanThreads) cur[k] = fsrc[k];
+        for (int k = fn + tid; k < fn + kWinPad && k < 65536 + kWinPad; k += kSpanThreads) cur[k] = 0;
+        TileEnv env;
+        env.w32 = reinterpret_cast<const uint32_t*>(S.win) + ((65536 - fs) >> 2);   // fs is a multiple of 65536
+        env.win = S.win + (65536 - fs);
+        env.gsrc = src; env.payload = out; env.pos0 = fs;
+        env.lo_valid = max(0, span_start - (sp != 0 ? 65536 : 0));
+        env.hash_end = min(n_blk - 4, fe - 4);                    // five bytes at p, all of them loaded
+        env.mf_end = warm ? fs : min(n_blk - MFLIMIT + 1, fe - 3);
+        env.match_end = min(n_blk - LASTLITERALS, fe);
+        env.ntiles = warm ? kMaxTiles : max(0, (env.mf_end - fs + kTile - 1) / kTile);
+        env.cap = 0x7FFFFFF0; env.parity = it & 1u; env.index_only = warm;
+        if (tid == 0) {
+            S.st_x[0] = carry_x; S.st_anchor[0] = carry_anchor; S.st_out[0] = carry_out;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (!bulk) mbar_arrive(&S.bar_load);
+            mbar_arrive(&S.bar_token[0]); mbar_arrive(&S.bar_entry[0]); mbar_arrive(&S.bar_out[0]);
+        }
+        mbar_wait(&S.bar_load, it & 1u);
+        run_worker<true, kSpanWorkers>(S, env, warp, lane, my_x);
+        __syncthreads();
+        if (!warm && env.ntiles > 0) {
+            carry_x = S.st_x[env.ntiles]; carry_anchor = S.st_anchor[env.ntiles]; carry_out = S.st_out[env.ntiles];
+        }
+        // barriers of tiles this fragment did not have stay one phase behind: only the last fragment of a block is short
+    }
+    if (tid == 0) {
+        span_len[w] = carry_out;                                  // bytes of sequences; the final literal run is the stitcher's
+        span_tail[w] = (uint32_t)(span_end - carry_anchor);
+    }
 }
-#endif
 
 cudaError_t configure_compress_cta()
 {
-    return cudaFuncSetAttribute(lz4_compress_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    cudaError_t e = cudaFuncSetAttribute(lz4_compress_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lz4_compress_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpanSmem));
+}
+
+cudaError_t launch_compress_spans(const EncodeArgs& a, uint8_t* tmp, uint32_t slot_stride, uint32_t spans_per_block, uint32_t span_bytes,
+                                  int32_t* span_len, uint32_t* span_tail, cudaStream_t stream)
+{
+    lz4_compress_span_kernel<<<a.nblk * spans_per_block, kSpanThreads, sizeof(SpanSmem), stream>>>(a, tmp, slot_stride, spans_per_block,
+                                                                                                   span_bytes, span_len, span_tail);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_compress_cta(const EncodeArgs& a, cudaStream_t stream)

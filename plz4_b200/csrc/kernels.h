@@ -48,6 +48,9 @@ cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream);
 // one CTA per block of <= 64 KiB, block staged in shared memory by TMA (compress_cta.cu); no dictionary
 cudaError_t launch_compress_cta(const EncodeArgs& a, cudaStream_t stream);
 cudaError_t configure_compress_cta();
+// blocks above 64 KiB: one CTA per span of 64 KiB fragments; the spans' streams (final literal run left out) go to tmp slots
+cudaError_t launch_compress_spans(const EncodeArgs& a, uint8_t* tmp, uint32_t slot_stride, uint32_t spans_per_block, uint32_t span_bytes,
+                                  int32_t* span_len, uint32_t* span_tail, cudaStream_t stream);
 cudaError_t configure_compress();     // one-time function attributes (opt-in shared memory)
 
 // dictionary table build (hash -> last position) for a given table size, device side

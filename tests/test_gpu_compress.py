@@ -58,6 +58,8 @@ def test_frame_records_layout(gpu, port, codec, bsz, checksum):
             assert n <= bsz
             r, data = codec.decompress(payload, bsz)
             assert r == len(b) and data == b
+        # per block, every kind, every block size (large blocks: liblz4 hashes five bytes there, lz4.c:785-795,1391-1400)
+        assert len(rec) <= max(len(ref_rec) * TOLERANCE, len(ref_rec) + 8), (i, len(rec), len(ref_rec))
         tot_gpu += len(rec)
         tot_ref += len(ref_rec)
     assert tot_gpu <= tot_ref * TOLERANCE
@@ -137,3 +139,33 @@ def test_compress_is_deterministic(gpu):
         if first is None:
             first = got
         assert got == first
+
+
+@pytest.mark.parametrize("n", [100000, 262144, 1 << 20, (4 << 20) + 12345])
+@pytest.mark.parametrize("kind", ["log", "words", "ab", "runs", "zeros", "record1025", "random"])
+def test_large_blocks_per_block_size_and_reference_decode(gpu, codec, kind, n):
+    """Blocks above 64 KiB (spans of fragments with the table and a 64 KiB window kept, compress_cta.cu): the reference decodes
+    every one and each stays within tolerance of liblz4 on the same block."""
+    s = make(kind, n, seed=5)
+    c = gpu.compress_block(s)
+    r, data = codec.decompress(c, n)
+    assert r == n and data == s
+    ref_c = codec.compress(s)
+    assert len(c) <= max(len(ref_c) * TOLERANCE, len(ref_c) + 8), (len(c), len(ref_c))
+
+
+def test_block_longer_than_the_room_offered(gpu, codec):
+    """plz4_block.go:100-109 WithBlockDst: the caller may offer less room than the block is long; a compressible block still
+    goes in whole (fragments are sized from the data, not from the room), an incompressible one is refused."""
+    s = make("log", 1 << 20, seed=8)
+    c = gpu.compress_block(s, dst_cap=600 << 10)
+    assert 0 < len(c) <= 600 << 10
+    back, data = codec.decompress(c, len(s))
+    assert back == len(s) and data == s
+    with pytest.raises(gpu.Lz4Error):
+        gpu.compress_block(make("random", 1 << 20, seed=8), dst_cap=600 << 10)
+    # just above the 66-fragment mark of the one-warp-per-fragment path
+    big = make("log", (4 << 20) + (200 << 10), seed=9)
+    c = gpu.compress_block(big)
+    back, data = codec.decompress(c, len(big))
+    assert back == len(big) and data == big

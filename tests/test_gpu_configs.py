@@ -132,3 +132,99 @@ def test_config2_device_resident_properties_at_scale(gpu, port):
         assert int.from_bytes(row[4 + c: 8 + c].tobytes(), "little") == port.xxh32(row[4: 4 + c].tobytes())
     ratio = float(rlen.to(torch.int64).sum()) / n
     assert 0.36 < ratio < 0.40
+
+
+# ---------------------------------------------------------------- the configs at their stated scale
+# Size-independent properties (round trip, checksum of checksums, the reference decodes a sample) at the sizes
+# BASELINE.json quotes: configs[0] 256 MiB, configs[2] 64 starts into a 1 GiB reference frame, configs[3] 1 Mi payloads.
+
+def test_config1_at_scale_256mib_4mib_blocks_both_checksums(gpu, port):
+    data = logtext(256 << 20, seed=21)
+    dst = io.BytesIO()
+    w = gpu.NewWriter(dst, block_size_idx=7, block_checksum=True, content_checksum=True, content_size=len(data))
+    assert w.read_from(io.BytesIO(data)) == len(data)
+    w.close()
+    frame = dst.getvalue()
+    assert F.read_frames(frame, port) == data                        # reference-format reader: every block + content checksum
+    out = io.BytesIO()
+    r = gpu.NewReader(io.BytesIO(frame))
+    assert r.write_to(out) == len(data)
+    r.close()
+    assert out.getbuffer().nbytes == len(data) and out.getvalue() == data
+    # per block within tolerance of liblz4 on the same block (64 blocks of 4 MiB)
+    pos, b = 7 + 8, 0
+    while True:
+        word = int.from_bytes(frame[pos:pos + 4], "little")
+        if word == 0:
+            break
+        n = word & 0x7FFFFFFF
+        ref_rec = port.block_record(data[b * (4 << 20):(b + 1) * (4 << 20)], 4 << 20, True)
+        assert 8 + n <= 1.03 * len(ref_rec), (b, n, len(ref_rec))
+        pos += 8 + n
+        b += 1
+    assert b == 64
+
+
+def test_config3_at_scale_64_starts_into_a_1gib_reference_frame(gpu, port):
+    bsz = 4 << 20
+    data = logtext(1 << 30, seed=22)
+    marks = []
+    frame = F.write_frame(data, F.Opts(block_idx=7, block_checksum=True, content_checksum=False), port,
+                          progress=lambda s, d: marks.append((s, d)))
+    assert len(marks) >= 256
+    rng = random.Random(5)
+    want = 32 << 20                                                  # bytes read from every start
+    for s, d in rng.sample(marks[:-1], 64):
+        r = gpu.NewReader(io.BytesIO(frame), read_offset=d)
+        got = bytearray()
+        while len(got) < want:
+            chunk = r.read(want - len(got))
+            if not chunk:
+                break
+            got += chunk
+        r.close()
+        assert bytes(got) == data[s:s + want], (s, d)
+
+
+def test_config4_at_scale_one_million_payloads_with_dictionary(gpu, port, codec):
+    torch = pytest.importorskip("torch")
+    L = gpu._lib.lib()
+    corpus = logtext(64 << 20, seed=23)
+    d = corpus[:65536]
+    nmsg, msz = 1 << 20, 4096
+    rng = np.random.default_rng(7)
+    starts = rng.integers(65536, len(corpus) - msz, size=nmsg).astype(np.int64)
+    gd, cd = gpu.Dict(d), codec.dict_create(d)
+    dev = torch.device("cuda", 0)
+    src = torch.frombuffer(bytearray(corpus), dtype=torch.uint8).to(dev)
+    off = torch.from_numpy(starts).to(dev)
+    ln = torch.full((nmsg,), msz, dtype=torch.int32, device=dev)
+    cap = gpu.compress_block_bound(msz)
+    stride = (cap + 15) // 16 * 16
+    recs = torch.empty(nmsg * stride, dtype=torch.uint8, device=dev)
+    rlen = torch.zeros(nmsg, dtype=torch.int32, device=dev)
+    out = torch.empty(nmsg * msz, dtype=torch.uint8, device=dev)
+    olen = torch.zeros(nmsg, dtype=torch.int32, device=dev)
+    roff = torch.arange(nmsg, dtype=torch.int64, device=dev) * stride
+    ooff = torch.arange(nmsg, dtype=torch.int64, device=dev) * msz
+    h_src = torch.zeros(nmsg, dtype=torch.int32, device=dev)
+    h_out = torch.zeros(nmsg, dtype=torch.int32, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    dh = gd.handle if hasattr(gd, "handle") else gd._h
+    gpu._lib.check(L.plz4cu_compress_batch_device(None, p(src), p(off), p(ln), nmsg, cap, 0, 1, dh, p(recs), stride, p(rlen)))
+    gpu._lib.check(L.plz4cu_decompress_batch_device(None, p(recs), p(roff), p(rlen), nmsg, msz, 0, 1, dh, p(out), msz, p(olen)))
+    gpu._lib.check(L.plz4cu_xxh32_batch_device(None, p(src), p(off), p(ln), nmsg, p(h_src)))
+    gpu._lib.check(L.plz4cu_xxh32_batch_device(None, p(out), p(ooff), p(ln), nmsg, p(h_out)))
+    torch.cuda.synchronize()
+    assert bool((rlen > 0).all()) and bool((olen == msz).all())
+    assert torch.equal(h_src, h_out)                                 # checksum of checksums: every payload came back
+    sample = rng.choice(nmsg, size=300, replace=False)
+    rl = rlen.cpu().numpy()
+    tot_gpu = tot_ref = 0
+    for i in sample:
+        m = corpus[int(starts[i]): int(starts[i]) + msz]
+        c = recs[int(i) * stride: int(i) * stride + int(rl[i])].cpu().numpy().tobytes()
+        assert cd.decompress(c, msz) == (msz, m)                     # the reference decodes it with the same dictionary
+        tot_gpu += len(c)
+        tot_ref += len(cd.compress(m))
+    assert tot_gpu <= 1.03 * tot_ref
