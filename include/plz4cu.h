@@ -7,7 +7,10 @@
  *
  * Memory contract: the kernels fetch whole aligned 4- and 16-byte words.  Device input buffers (sources, records,
  * dictionaries) must therefore be readable up to the next 16-byte boundary after their last byte — true for every
- * CUDA allocation; nothing past that boundary is touched (profiles/r01_sanitizer.txt).  Outputs are written exactly.
+ * CUDA allocation; nothing past that boundary is touched (profiles/r01_sanitizer.txt).  Device outputs are written
+ * exactly (a record slot up to its record length, an output slot up to the decoded length).  The HOST decompress entry
+ * points copy whole dst_cap-wide slots back: bytes of a slot beyond out_len[b], and the whole slot of a failed block,
+ * are unspecified (they come from a scratch buffer the engine reuses) — read out_len[b] bytes, no more.
  *
  * Block record layout (identical to blk.CompressToBlk, internal/pkg/blk/blk.go:87-106):
  *     [ LE32 size | bit31 = stored uncompressed ][ payload ][ LE32 xxh32(payload) if block checksum ]
@@ -182,8 +185,10 @@ PLZ4CU_API int plz4cu_decompress_frame_device(plz4cu_stream_t stream, const void
                                    uint64_t* rec_off, int32_t* out_len, uint32_t cap, plz4cu_frame_info_t* info);
 
 /* The writer's side of the same: n device-resident bytes become ONE complete LZ4 frame in device memory (header,
- * block records in order as async/writer.go:316-348 would write them, EndMark) — byte for byte what NewWriter produces
- * from the same bytes and options.  Honoured options: block size, block checksum, content size, dictionary id; level
+ * block records in order as async/writer.go:316-348 would write them, EndMark) — byte for byte what THIS library's
+ * NewWriter produces from the same bytes and options, and decodable by any LZ4 frame reader.  It is NOT bit-exact with
+ * plz4 / liblz4 output: the parse differs (sizes within the stated tolerance), so do not compare or deduplicate
+ * compressed bytes across the two.  Honoured options: block size, block checksum, content size, dictionary id; level
  * must be 1 and blocks independent.  A content checksum is refused with PLZ4CU_Z_UNSUPPORTED: it is a serial xxh32 of
  * the whole input and stays a host-side job.  frame_cap: header + ceil(n/bsz)*(bsz+8) + 4 always suffices; returns
  * PLZ4CU_ERR_ARG when the frame does not fit.  Synchronous. */

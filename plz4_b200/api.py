@@ -184,8 +184,9 @@ def decompress_frame_device(frame, *, dict: Dict | None = None, stream=None):
 
 
 def compress_frame_device(src, *, dict: Dict | None = None, stream=None, **options):
-    """n bytes of a CUDA uint8 tensor -> one complete LZ4 frame in a CUDA uint8 tensor, byte for byte what NewWriter
-    writes for the same bytes and options (block_size_idx, block_checksum, content_size, dict_id; no content checksum)."""
+    """n bytes of a CUDA uint8 tensor -> one complete LZ4 frame in a CUDA uint8 tensor, byte for byte what this library's
+    NewWriter writes for the same bytes and options (block_size_idx, block_checksum, content_size, dict_id; no content
+    checksum).  Any LZ4 frame reader decodes it; the bytes are not those plz4 / liblz4 would write (the parse differs)."""
     import torch
     from .stream import StreamError, _opts
     L = _lib.lib()

@@ -28,6 +28,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <new>
 #include <vector>
 
 namespace {
@@ -692,11 +693,26 @@ struct plz4cu_reader {
                 r = read_full(h + 7, 1, &got);
                 src_pos += (int64_t)got;
                 if (r != 0) return PLZ4CU_Z_HEADER_READ;
+                // The size comes from the stream: never allocate on its say-so.  Without a callback the payload is read
+                // and dropped 64 KiB at a time (header/skip.go: io.CopyN(io.Discard)); with one the buffer grows only as
+                // bytes really arrive, and an allocation failure is this frame's error, not the process's end.
                 uint32_t sz = get32(h + 4);
-                std::vector<uint8_t> payload(sz);
-                r = read_full(payload.data(), sz, &got);
-                src_pos += (int64_t)got;
-                if (r != 0 && sz) return PLZ4CU_Z_SKIP;
+                std::vector<uint8_t> payload;
+                try {
+                    const size_t kPiece = 64u << 10;
+                    if (!opt.o.skip_cb) payload.resize((size_t)std::min<uint64_t>(sz, kPiece));
+                    for (uint64_t done = 0; done < sz;) {
+                        const size_t want = (size_t)std::min<uint64_t>(sz - done, kPiece);
+                        uint8_t* at = payload.data();
+                        if (opt.o.skip_cb) { payload.resize((size_t)done + want); at = payload.data() + done; }
+                        r = read_full(at, want, &got);
+                        src_pos += (int64_t)got;
+                        if (r != 0) return PLZ4CU_Z_SKIP;
+                        done += want;
+                    }
+                } catch (const std::bad_alloc&) {
+                    return PLZ4CU_Z_SKIP;
+                }
                 if (opt.o.skip_cb && opt.o.skip_cb(opt.o.skip_ctx, (uint8_t)(m & 0xF), payload.data(), sz) != 0) return PLZ4CU_Z_SKIP;
                 continue;                               // a skipped frame puts the reader back in header mode
             }

@@ -211,6 +211,20 @@ def test_concatenated_and_skip_frames(gpu):
     with pytest.raises(gpu.StreamError) as e:
         gpu.write_skip_frame_header(io.BytesIO(), 16, 0)
     assert e.value.name == "ErrNibble"
+    # a skip frame that claims 4 GiB and delivers ten bytes: ErrSkip, without the reader allocating what the header says
+    # (header/skip.go:38-76 streams the payload), with and without a callback; a 200 KiB payload arrives whole
+    liar = bytes.fromhex("532a4d18f0ffffff") + b"0123456789"
+    for cb in (None, lambda nib, p: None):
+        with pytest.raises(gpu.StreamError) as e:
+            decompress(gpu, fa + liar, skip_callback=cb)
+        assert e.value.name == "ErrSkip"
+    big = bytes(range(256)) * 800
+    hdr = io.BytesIO()
+    gpu.write_skip_frame_header(hdr, 2, len(big))
+    seen = []
+    assert decompress(gpu, hdr.getvalue() + big + fb, skip_callback=lambda nib, p: seen.append((nib, p))) == b
+    assert seen == [(2, big)]
+    assert decompress(gpu, hdr.getvalue() + big + fb) == b
 
 
 def test_dictionary_frames(gpu, port):
