@@ -389,7 +389,11 @@ __device__ __forceinline__ void run_worker(SM& S, const TileEnv& C, int pw, int 
                     // 16-bit arithmetic: a group never straddles a multiple of 65536
                     const uint32_t g16 = (uint32_t)(tile_base + 32 * (gb + j)) & 0xFFFFu;
                     const uint32_t hw = __shfl_sync(FULL_MASK, h[j], (int)(w[j] & 31u));
-                    if (w[j] >= g16 && w[j] < g16 + (uint32_t)lane && hw == h[j]) {
+                    // An even position below this one, in this group, hashed like it: then its lane stored into this very
+                    // slot a moment ago, so what was read is this group's (never what an earlier tile or an earlier CTA
+                    // left in the scratch, which would make the choice of candidate depend on history).
+                    if (w[j] >= g16 && w[j] < g16 + (uint32_t)lane && (w[j] & 1u) == 0 && hw == h[j] &&
+                        tile_base + 32 * (gb + j) + (int)(w[j] & 31u) < hash_end) {
                         c[j] = w[j];
                         pg[j * kPvStride] = (uint16_t)w[j];
                     }

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -132,6 +133,87 @@ void bulk_copy(void* dst, const void* src, size_t n)
     }
 #endif
     memcpy(dst, src, n);
+}
+
+// One thread moves 12-14 GB/s; the PCIe link behind the staging moves four times that.  Copies of 8 MiB and more are cut
+// into pieces for a small pool of helper threads (the caller takes the first piece), so a stream fed from pageable memory
+// is no longer bound by one core's memcpy (async/writer.go:81-107 has the same shape: the caller only slices, workers do
+// the rest).  PLZ4CU_COPY_THREADS sets the number of helpers (default 3, 0 = none).
+class CopyPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    bool stop = false;
+public:
+    explicit CopyPool(int n)
+    {
+        for (int i = 0; i < n; i++) th.emplace_back([this] {
+            std::unique_lock<std::mutex> lk(mu);
+            for (;;) {
+                cv.wait(lk, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                std::function<void()> f = std::move(q.front());
+                q.pop_front();
+                lk.unlock();
+                f();
+                lk.lock();
+            }
+        });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+    size_t size() const { return th.size(); }
+    void submit(std::function<void()> f)
+    {
+        { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(f)); }
+        cv.notify_one();
+    }
+};
+
+CopyPool& copy_pool()
+{
+    static CopyPool* pool = [] {
+        int n = 3;
+        if (const char* e = getenv("PLZ4CU_COPY_THREADS")) n = std::max(0, std::min(32, atoi(e)));
+        return new CopyPool(n);                             // lives as long as the process: streams may end at exit
+    }();
+    return *pool;
+}
+
+void bulk_copy_mt(void* dst, const void* src, size_t n, int site = 0)
+{
+    static const int sites = getenv("PLZ4CU_COPY_SITES") ? atoi(getenv("PLZ4CU_COPY_SITES")) : 15;
+    if (!(sites & site)) { bulk_copy(dst, src, n); return; }
+    constexpr size_t kMin = 8u << 20, kPiece = 2u << 20;
+    CopyPool& pool = copy_pool();
+    if (n < kMin || pool.size() == 0) { bulk_copy(dst, src, n); return; }
+    const size_t parts = std::min(pool.size() + 1, n / kPiece);
+    const size_t per = ((n / parts) + 4095) & ~size_t(4095);
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t left = 0;
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    const uint8_t* s = static_cast<const uint8_t*>(src);
+    for (size_t off = per; off < n; off += per) {
+        const size_t len = std::min(per, n - off);
+        { std::lock_guard<std::mutex> lk(mu); left++; }
+        pool.submit([&, off, len] {
+            bulk_copy(d + off, s + off, len);
+            std::lock_guard<std::mutex> lk(mu);
+            if (--left == 0) cv.notify_all();
+        });
+    }
+    bulk_copy(d, s, std::min(per, n));
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return left == 0; });
+    static const bool check = getenv("PLZ4CU_COPY_CHECK") != nullptr;
+    if (check && memcmp(dst, src, n) != 0) { fprintf(stderr, "bulk_copy_mt: MISMATCH n=%zu site=%d\n", n, site); abort(); }
+    if (check) fprintf(stderr, "bulk_copy_mt ok n=%zu site=%d parts=%zu\n", n, site, parts);
 }
 
 int current_device()
@@ -514,7 +596,7 @@ struct plz4cu_writer {
             size_t take = 0;
             uint8_t* dst = stage_space(n - done, &take);
             if (!dst) { set_error(PLZ4CU_Z_ENGINE); break; }
-            bulk_copy(dst, src + done, take);
+            bulk_copy_mt(dst, src + done, take, 1);
             done += take;
             stage_commit(take);
         }
@@ -1011,7 +1093,7 @@ struct plz4cu_reader {
             for (;;) {
                 if (have_block && cur_off < cur_len) {
                     size_t k = std::min(n - produced, cur_len - cur_off);
-                    bulk_copy(dst + produced, block_ptr() + cur_off, k);
+                    bulk_copy_mt(dst + produced, block_ptr() + cur_off, k, 2);
                     cur_off += k; produced += k;
                     if (produced == n) return (int64_t)produced;
                 }
@@ -1174,7 +1256,7 @@ int64_t plz4cu_membuf_read(void* ctx, void* buf, size_t n)
 {
     plz4cu_membuf* m = static_cast<plz4cu_membuf*>(ctx);
     size_t k = std::min(n, m->len - m->pos);
-    bulk_copy(buf, m->data + m->pos, k);
+    bulk_copy_mt(buf, m->data + m->pos, k, 4);
     m->pos += k;
     return (int64_t)k;
 }
@@ -1182,7 +1264,7 @@ int64_t plz4cu_membuf_write(void* ctx, const void* data, size_t n)
 {
     plz4cu_membuf* m = static_cast<plz4cu_membuf*>(ctx);
     if (m->len + n > m->cap) return -1;
-    bulk_copy(m->data + m->len, data, n);
+    bulk_copy_mt(m->data + m->len, data, n, 8);
     m->len += n;
     return (int64_t)n;
 }

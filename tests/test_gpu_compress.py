@@ -133,7 +133,7 @@ def test_compress_is_deterministic(gpu):
     blocks = [logtext(bsz, seed=1000 + i) for i in range(48)] + [make(k, bsz, seed=3) for k in ["words", "runs", "ab", "zeros", "record1025", "random"]] * 4
     buf, off = b"".join(blocks), np.arange(len(blocks), dtype=np.uint64) * bsz
     first = None
-    for _ in range(4):
+    for _ in range(16):
         packed, poff = gpu.compress_batch(buf, off, [bsz] * len(blocks), bsz, block_checksum=True)
         got = (packed[: int(poff[-1])].tobytes(), poff.tobytes())
         if first is None:
