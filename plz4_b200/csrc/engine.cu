@@ -55,8 +55,8 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess)
 constexpr int kMaxLanes = 8;
 int kLanes = 4;                                  // lanes in use                   (PLZ4CU_LANES)
 bool g_spin_wait = false;                        // busy-wait on the GPU instead of sleeping (PLZ4CU_SPIN, measurements)
-uint32_t kChunkBlocks = 2048;                    // blocks per chunk we aim for    (PLZ4CU_CHUNK_BLOCKS)
-const uint64_t kChunkMinBytes = 64ull << 20;     // ... but small payloads are gathered up to this many bytes
+uint32_t kChunkBlocks = 256;                     // blocks per chunk we aim for    (PLZ4CU_CHUNK_BLOCKS)
+uint64_t kChunkMinBytes = 16ull << 20;           // ... but small payloads are gathered up to this many bytes (PLZ4CU_CHUNK_MIB)
 const uint64_t kChunkBytes = 512ull << 20;       // upper bound on a chunk's input span
 
 void read_tuning_env()
@@ -66,6 +66,7 @@ void read_tuning_env()
         if (const char* e = getenv("PLZ4CU_LANES")) { int v = atoi(e); if (v >= 1 && v <= kMaxLanes) kLanes = v; }
         if (const char* e = getenv("PLZ4CU_CHUNK_BLOCKS")) { int v = atoi(e); if (v >= 1) kChunkBlocks = (uint32_t)v; }
         if (const char* e = getenv("PLZ4CU_SPIN")) g_spin_wait = atoi(e) != 0;
+        if (const char* e = getenv("PLZ4CU_CHUNK_MIB")) { int v = atoi(e); if (v >= 1) kChunkMinBytes = (uint64_t)v << 20; }
     });
 }
 
@@ -600,9 +601,10 @@ int plz4cu_compress_frame_device(plz4cu_stream_t stream, const void* src, uint64
 //
 // Blocks are cut into chunks and software-pipelined over kLanes lanes (stream + private scratch
 // each), so that the H2D of chunk k, the kernels of chunk k-1 and the D2H of chunk k-2 overlap.
-// A chunk must hold enough blocks to fill the GPU on its own — one warp works on one block for
-// milliseconds, so a launch with fewer blocks than resident warps (148 SMs x 24..36) runs at a
-// fraction of the kernel's throughput — hence the block-count target, capped by bytes.
+// A chunk is 16 MiB and 256 blocks at least: the encoder gives every block (or span of a large block) a CTA that
+// is done in a fraction of a millisecond, so a launch of that size fills the GPU for long enough, chunks of
+// different lanes run side by side, and a 64 MiB batch of a stream already pipelines over the lanes (it was one
+// chunk when a warp worked on a block for milliseconds and a chunk had to bring thousands of blocks).
 // All small metadata crosses PCIe through pinned staging, so no call in the loop blocks the host
 // except the explicit waits.
 
@@ -627,7 +629,11 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
     const uint8_t* hsrc = static_cast<const uint8_t*>(src);
     uint8_t* hout = static_cast<uint8_t*>(packed);
     uint32_t max_len = 0;
-    for (uint32_t b = 0; b < nblk; b++) max_len = std::max(max_len, src_len[b]);
+    uint64_t total_len = 0;
+    for (uint32_t b = 0; b < nblk; b++) { max_len = std::max(max_len, src_len[b]); total_len += src_len[b]; }
+    // a chunk is an eighth of the call, between kChunkMinBytes (16 MiB: a stream's 64 MiB batch still pipelines over the
+    // lanes) and 64 MiB (a whole buffer is not cut finer than its copies need: every chunk costs two host waits)
+    const uint64_t chunk_min = std::min<uint64_t>(std::max<uint64_t>(total_len / 8, kChunkMinBytes), std::max<uint64_t>(kChunkMinBytes, 64ull << 20));
     const uint32_t slot_payload = std::max(dst_cap, max_len);
     const uint32_t stride = round_up16(slot_payload + (raw_blocks ? 0 : PLZ4CU_REC_OVERHEAD));
 
@@ -636,7 +642,7 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         Chunk c{b, b, src_off[b], src_off[b] + src_len[b]};
         while (c.b1 < nblk) {
             uint64_t lo = std::min(c.lo, src_off[c.b1]), hi = std::max(c.hi, src_off[c.b1] + src_len[c.b1]);
-            if (c.b1 > c.b0 && (hi - lo > kChunkBytes || (c.b1 - c.b0 >= kChunkBlocks && c.hi - c.lo >= kChunkMinBytes))) break;
+            if (c.b1 > c.b0 && (hi - lo > kChunkBytes || (c.b1 - c.b0 >= kChunkBlocks && c.hi - c.lo >= chunk_min))) break;
             c.lo = lo; c.hi = hi; c.b1++;
         }
         chunks.push_back(c);
@@ -748,7 +754,9 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
     };
 
     std::vector<Chunk> chunks;
-    const uint32_t max_blk_per_chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(kChunkBlocks, kChunkMinBytes / std::max<uint32_t>(dst_cap, 1)),
+    const uint64_t total_out = (uint64_t)nblk * dst_cap;
+    const uint64_t chunk_min = std::min<uint64_t>(std::max<uint64_t>(total_out / 8, kChunkMinBytes), std::max<uint64_t>(kChunkMinBytes, 64ull << 20));
+    const uint32_t max_blk_per_chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(kChunkBlocks, chunk_min / std::max<uint32_t>(dst_cap, 1)),
                                                                     std::max<uint64_t>(1, kChunkBytes / std::max<uint32_t>(dst_cap, 1)));
     for (uint32_t b = 0; b < nblk;) {
         uint64_t lo, hi;

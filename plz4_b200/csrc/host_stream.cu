@@ -135,7 +135,7 @@ void bulk_copy(void* dst, const void* src, size_t n)
     memcpy(dst, src, n);
 }
 
-// One thread moves 12-14 GB/s; the PCIe link behind the staging moves four times that.  Copies of 8 MiB and more are cut
+// One thread moves 12-14 GB/s; the PCIe link behind the staging moves four times that.  Copies of 1 MiB and more are cut
 // into pieces for a small pool of helper threads (the caller takes the first piece), so a stream fed from pageable memory
 // is no longer bound by one core's memcpy (async/writer.go:81-107 has the same shape: the caller only slices, workers do
 // the rest).  PLZ4CU_COPY_THREADS sets the number of helpers (default 3, 0 = none).
@@ -189,7 +189,7 @@ void bulk_copy_mt(void* dst, const void* src, size_t n, int site = 0)
 {
     static const int sites = getenv("PLZ4CU_COPY_SITES") ? atoi(getenv("PLZ4CU_COPY_SITES")) : 15;
     if (!(sites & site)) { bulk_copy(dst, src, n); return; }
-    constexpr size_t kMin = 8u << 20, kPiece = 2u << 20;
+    constexpr size_t kMin = 1u << 20, kPiece = 256u << 10;
     CopyPool& pool = copy_pool();
     if (n < kMin || pool.size() == 0) { bulk_copy(dst, src, n); return; }
     const size_t parts = std::min(pool.size() + 1, n / kPiece);
@@ -872,49 +872,96 @@ struct plz4cu_reader {
     }
 
     // blk/frame.go:54-112 for up to `want_bytes` of blocks: the records of one batch, in order (source thread).
+    // Bytes read past the last record of a batch while the body goes on (bulk reads, below); they open the next batch.
+    std::vector<uint8_t> carry;
+
     void read_records(Batch& b, size_t want_bytes)
     {
         const size_t batch_blocks = std::max<size_t>(1, want_bytes / (size_t)bsz);
         b.recs_len = 0; b.rec_off.clear(); b.rec_read.clear();
         b.nblk = 0; b.tail_event = 0; b.tail_read = 0; b.hash_ticket = 0; b.ticket = 0;
         uint32_t nblk = 0;
+        // The reference reads a size word, then a body, block after block (blk/frame.go:54-112) — two small reads per
+        // block, which one thread cannot do faster than a few GB/s.  When the source can seek, the record area is filled
+        // in pieces of up to 8 MiB instead (one read callback each, copied by several threads when it comes from memory)
+        // and walked in place; what was read beyond the batch is kept for the next one, and what was read beyond the
+        // frame is given back with one seek, so the source stands exactly where the reference would leave it.
+        const bool bulk = async && seek != nullptr;
+        const size_t cap_max = batch_blocks * ((size_t)bsz + 8) + 64 + (bulk ? (9u << 20) : 0);
+        size_t fill = 0;                                // bytes of the stream sitting in b.recs
+        bool eof = false, failed = false;
+        auto room_for = [&](size_t upto) -> bool {
+            if (upto <= b.recs.cap) return true;
+            return b.recs.grow(std::min(cap_max, std::max(upto, 2 * b.recs.cap)), fill);
+        };
+        if (bulk && !carry.empty()) {
+            if (!room_for(carry.size())) { b.tail_event = PLZ4CU_Z_ENGINE; b.nblk = 0; return; }
+            memcpy(b.recs.p, carry.data(), carry.size());
+            fill = carry.size();
+            carry.clear();
+        }
+        // make stream bytes [0, upto) present in b.recs; false = the stream ended (or failed) first
+        auto need = [&](size_t upto) -> bool {
+            while (fill < upto && !eof) {
+                if (!bulk) {
+                    size_t got = 0;
+                    const int r = read_full(b.recs.p + fill, upto - fill, &got);
+                    fill += got;
+                    if (r != 0) { eof = true; failed = r < 0; }
+                    break;
+                }
+                const size_t piece = std::max<size_t>(upto - fill, std::min<size_t>(8u << 20, std::max<size_t>(64u << 10, b.recs.cap - fill)));
+                if (!room_for(fill + piece)) { eof = true; failed = true; break; }
+                const int64_t r = rd(ctx, b.recs.p + fill, std::min(piece, b.recs.cap - fill));
+                if (r <= 0) { eof = true; failed = r < 0; break; }
+                fill += (size_t)r;
+            }
+            return fill >= upto;
+        };
         while (nblk < batch_blocks) {
-            uint8_t w[4];
-            size_t got = 0;
-            int r = read_full(w, 4, &got);
-            if (r != 0) { b.tail_event = PLZ4CU_Z_BLOCK_SIZE_READ; b.tail_read = (uint32_t)got; break; }
-            uint32_t word = get32(w);
+            const size_t at = b.recs_len;
+            if (!room_for(at + 4)) { b.tail_event = PLZ4CU_Z_ENGINE; break; }
+            if (!need(at + 4)) { b.tail_event = PLZ4CU_Z_BLOCK_SIZE_READ; b.tail_read = (uint32_t)(fill - at); b.recs_len = fill; break; }
+            const uint32_t word = get32(b.recs.p + at);
             if (word == 0) {                            // EndMark (+ content checksum)
                 b.endmark_read = 4;
                 b.tail_event = 2;
+                b.recs_len = at + 4;
                 if (has_content_hash) {
-                    uint8_t c[4];
-                    r = read_full(c, 4, &got);
-                    b.endmark_read += (uint32_t)got;
-                    if (r != 0) { b.tail_event = PLZ4CU_Z_CONTENT_HASH_READ; b.tail_read = b.endmark_read; break; }
-                    b.content_hash_read = get32(c);
+                    if (!room_for(at + 8) || !need(at + 8)) {
+                        b.endmark_read += (uint32_t)(fill - (at + 4));
+                        b.tail_event = PLZ4CU_Z_CONTENT_HASH_READ; b.tail_read = b.endmark_read;
+                        b.recs_len = fill;
+                        break;
+                    }
+                    b.endmark_read += 4;
+                    b.content_hash_read = get32(b.recs.p + at + 4);
+                    b.recs_len = at + 8;
                 }
                 break;
             }
-            uint32_t n = word & 0x7FFFFFFFu;
-            if (n > (uint32_t)bsz) { b.tail_event = PLZ4CU_Z_BLOCK_SIZE_OVERFLOW; b.tail_read = 4; break; }
+            const uint32_t n = word & 0x7FFFFFFFu;
+            if (n > (uint32_t)bsz) { b.tail_event = PLZ4CU_Z_BLOCK_SIZE_OVERFLOW; b.tail_read = 4; b.recs_len = at + 4; break; }
             const size_t body = (size_t)n + (blk_check ? 4 : 0);
-            const size_t at = b.recs_len;
             // the record area grows with what actually arrives (a short stream never pins a full batch)
-            if (at + 4 + body > b.recs.cap &&
-                !b.recs.grow(std::min(batch_blocks * ((size_t)bsz + 8), std::max(at + 4 + body, 2 * b.recs.cap)), at)) {
-                b.tail_event = PLZ4CU_Z_ENGINE;
-                break;
-            }
-            memcpy(b.recs.p + at, w, 4);
-            r = read_full(b.recs.p + at + 4, body, &got);
-            if (r != 0) { b.tail_event = PLZ4CU_Z_BLOCK_READ; b.tail_read = 4 + (uint32_t)got; break; }
+            if (!room_for(at + 4 + body)) { b.tail_event = PLZ4CU_Z_ENGINE; break; }
+            if (!need(at + 4 + body)) { b.tail_event = PLZ4CU_Z_BLOCK_READ; b.tail_read = (uint32_t)(fill - at); b.recs_len = fill; break; }
             b.recs_len = at + 4 + body;
             b.rec_off.push_back(at);
             b.rec_read.push_back((uint32_t)(4 + body));
             nblk++;
         }
         b.nblk = nblk;
+        if (bulk && fill > b.recs_len) {
+            const size_t extra = fill - b.recs_len;
+            if (b.tail_event == 0) carry.assign(b.recs.p + b.recs_len, b.recs.p + fill);        // the body goes on
+            else if (seek(ctx, -(int64_t)extra) != 0) { b.tail_event = PLZ4CU_Z_ENGINE; }        // past the frame: give it back
+        }
+        if (b.tail_event != 0) {
+            // the records end where the last whole one ends (what follows is the tail event's own bytes)
+            b.recs_len = b.rec_off.empty() ? 0 : (size_t)b.rec_off.back() + b.rec_read.back();
+        }
+        (void)failed;
     }
     // one engine call for the batch (the slot's engine thread when async)
     void decode_records(Batch& b)
@@ -949,8 +996,8 @@ struct plz4cu_reader {
         next_batch_bytes = std::min(limit, next_batch_bytes * 4);
         return want;
     }
-    // batches decoding ahead of the caller: one for small blocks (a batch fills the GPU), more for large ones
-    int read_ahead_depth() const { return bsz >= (1 << 20) ? kSlots - 1 : 1; }
+    // batches ahead of the caller: three for small blocks (one being read, one decoding, one ready), more for large ones
+    int read_ahead_depth() const { return bsz >= (1 << 20) ? kSlots - 1 : std::min(kSlots - 1, 3); }
     // source thread: read batch after batch in order, hand each to its slot's engine thread, stay at most
     // read_ahead_depth() batches ahead of the caller; ends with the batch that carries the body's tail event
     void source_loop()
@@ -990,7 +1037,7 @@ struct plz4cu_reader {
             read_records(bt[0], next_fill_bytes());
             decode_records(bt[0]);
             next = 0;
-        } else if (!have_batch && read_ahead_depth() == 1) {
+        } else if (!have_batch && bsz < (1 << 20)) {
             Batch& b = bt[0];
             if (b.hash_ticket) hash_q.wait(b.hash_ticket);
             read_records(b, next_fill_bytes());
@@ -1141,6 +1188,7 @@ struct plz4cu_reader {
         if (closed) return state;                       // rdr/rdr.go:109-112: a second Close reports the state (ErrClosed)
         closed = true;
         quiesce();                                      // the source callback is not used after Close
+        if (!carry.empty() && seek) { seek(ctx, -(int64_t)carry.size()); carry.clear(); }   // closed inside a body: give back what was read ahead
         if (state == 0 || state == 1) state = PLZ4CU_Z_CLOSED;
         return 0;
     }

@@ -301,3 +301,33 @@ def test_random_read_sizes_large_stream(gpu, port):
         out += chunk
     r.close()
     assert bytes(out) == data
+
+
+def test_reader_leaves_the_source_where_the_frame_ends(gpu):
+    """The reader fills its record area in large reads when the source can seek and gives back what it read past the
+    frame, so bytes that follow an LZ4 frame in the same source are still there for the caller (the reference reads
+    block by block and never runs ahead, blk/frame.go:54-112)."""
+    data = make("log", 3_000_000, seed=31)
+    for opts in (dict(block_size_idx=4, block_checksum=True), dict(block_size_idx=5, content_checksum=True)):
+        frame = compress(gpu, data, **opts)
+        trailer = b"TRAILING BYTES THAT ARE NOT LZ4" * 1000
+        src = io.BytesIO(frame + trailer)
+        r = gpu.NewReader(src)
+        got = bytearray()
+        while len(got) < len(data):
+            chunk = r.read(len(data) - len(got))
+            assert chunk
+            got += chunk
+        assert bytes(got) == data
+        # io.Reader semantics: the frame's end is only seen by the read that finds the EndMark; ask for it
+        with pytest.raises(gpu.StreamError):
+            r.read(1)                                       # what follows is not a frame header: ErrMagic
+        r.close()
+    # closing inside a body also puts the source back
+    frame = compress(gpu, data, block_size_idx=4)
+    src = io.BytesIO(frame)
+    r = gpu.NewReader(src)
+    first = r.read(100_000)
+    assert first == data[:100_000]
+    r.close()
+    assert src.tell() <= len(frame)
