@@ -68,6 +68,15 @@ typedef void* plz4cu_stream_t;           /* a cudaStream_t; NULL = the legacy de
 PLZ4CU_API int plz4cu_device_count(void);
 /* Bind the calling thread to `device` and warm the context.  0 or a negative PLZ4CU_ERR_*. */
 PLZ4CU_API int plz4cu_init(int device);
+/* Register the devices ONE stream may spread its batches over (whole independent blocks are sharded
+ * across the GPUs of a box, no collective): warms every context and leaves the calling thread on devs[0].  A writer or
+ * reader opened with opts.n_devices > 1 (or -1: all of them) then cuts every batch into contiguous runs of blocks, one
+ * run per device, each on its own pipeline; the dictionary is replicated per device and the bytes produced are those of
+ * the one-GPU stream.  The reference's fan-out over N workers (async/writer.go:439-467 via opts.WorkerPool.Submit,
+ * opts/opts.go:43-45) is the model.  0 or a negative PLZ4CU_ERR_*. */
+PLZ4CU_API int plz4cu_init_devices(int ndev, const int* devs);
+/* Devices registered by plz4cu_init_devices (0 if it was never called). */
+PLZ4CU_API int plz4cu_registered_devices(void);
 /* Text of the last failure on this thread ("" if none). */
 PLZ4CU_API const char* plz4cu_last_error(void);
 /* "plz4cu <version> sm_100a" */
@@ -268,6 +277,8 @@ PLZ4CU_API int plz4cu_xxh32_batch_device(plz4cu_stream_t stream, const void* bas
 typedef int64_t (*plz4cu_write_fn)(void* ctx, const void* data, size_t n);
 typedef int64_t (*plz4cu_read_fn)(void* ctx, void* buf, size_t n);
 typedef int     (*plz4cu_seek_fn)(void* ctx, int64_t delta);
+/* opts.WorkerPool.Submit (internal/pkg/opts/opts.go:43-45): run task(arg) on a worker; 0 = accepted. */
+typedef int     (*plz4cu_submit_fn)(void* ctx, void (*task)(void*), void* arg);
 /* opts.ProgressFuncT (plz4_opts.go:113-124): (src_block_offset, dst_block_offset) at every block boundary. */
 typedef void    (*plz4cu_progress_fn)(void* ctx, int64_t src_off, int64_t dst_off);
 /* opts.SkipCallbackT: called with a skippable frame's payload (already read: at most sz bytes). */
@@ -292,10 +303,15 @@ typedef struct plz4cu_opts {
     size_t   dict_len;
     int64_t  read_offset;        /* WithReadOffset                                                         */
     int32_t  content_size_check; /* WithContentSizeCheck                                                   */
-    int32_t  reserved0;
+    int32_t  n_devices;          /* 0 / 1: the calling thread's device; N > 1: the first N devices registered by   */
+                                 /*   plz4cu_init_devices; -1: all of them                                          */
     plz4cu_progress_fn progress; void* progress_ctx;   /* WithProgress      */
     plz4cu_skip_fn     skip_cb;  void* skip_ctx;       /* WithSkipCallback  */
     plz4cu_dict_fn     dict_cb;  void* dict_ctx;       /* WithDictCallback  */
+    plz4cu_submit_fn   submit;   void* submit_ctx;     /* WithWorkerPool (plz4_opts.go:107, opts/opts.go:43-45,97-104): the    */
+                                 /*   stream's long-running stages (engine, sink / source, content hash) are handed to    */
+                                 /*   submit(submit_ctx, task, arg), which must run task(arg) on some thread and may       */
+                                 /*   return at once; NULL = the stream starts its own threads (opts.StubWorkerPool)      */
 } plz4cu_opts_t;
 
 /* parseOpts defaults (plz4_opts.go:238-255): level 1, parallel 1, 4 MiB blocks, content checksum on. */

@@ -6,6 +6,6 @@ this package is the thin host-side mirror of the reference interface used by tes
 from . import _lib  # noqa: F401
 from .api import (  # noqa: F401
     Dict, Lz4Error, Plz4cuError, compress_batch, compress_block, compress_block_bound, compress_frame_device,
-    decompress_batch, decompress_block, decompress_frame_device, init, lz4_corrupted,
+    decompress_batch, decompress_block, decompress_frame_device, device_count, init, init_devices, lz4_corrupted,
 )
 from .stream import NewReader, NewWriter, Reader, StreamError, Writer, write_skip_frame_header  # noqa: F401,E402

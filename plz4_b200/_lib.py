@@ -28,6 +28,8 @@ _vp, _u32, _u64, _i32, _int, _sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
 SIGNATURES = {
     "plz4cu_device_count": (_int, []),
     "plz4cu_init": (_int, [_int]),
+    "plz4cu_init_devices": (_int, [_int, C.POINTER(C.c_int)]),
+    "plz4cu_registered_devices": (_int, []),
     "plz4cu_last_error": (C.c_char_p, []),
     "plz4cu_version": (C.c_char_p, []),
     "plz4cu_launch_count": (_u64, []),
@@ -84,6 +86,8 @@ SIGNATURES = {
 WRITE_FN = C.CFUNCTYPE(C.c_int64, _vp, _vp, _sz)
 READ_FN = C.CFUNCTYPE(C.c_int64, _vp, _vp, _sz)
 SEEK_FN = C.CFUNCTYPE(_int, _vp, C.c_int64)
+TASK_FN = C.CFUNCTYPE(None, _vp)
+SUBMIT_FN = C.CFUNCTYPE(_int, _vp, TASK_FN, _vp)
 PROGRESS_FN = C.CFUNCTYPE(None, _vp, C.c_int64, C.c_int64)
 SKIP_FN = C.CFUNCTYPE(_int, _vp, C.c_uint8, _vp, _u32)
 DICT_FN = C.CFUNCTYPE(_int, _vp, _u32, C.POINTER(_vp), C.POINTER(_sz))
@@ -97,10 +101,11 @@ class Opts(C.Structure):
         ("has_content_size", C.c_int32), ("content_size", C.c_uint64),
         ("has_dict_id", C.c_int32), ("dict_id", C.c_uint32),
         ("dict", _vp), ("dict_len", _sz),
-        ("read_offset", C.c_int64), ("content_size_check", C.c_int32), ("reserved0", C.c_int32),
+        ("read_offset", C.c_int64), ("content_size_check", C.c_int32), ("n_devices", C.c_int32),
         ("progress", PROGRESS_FN), ("progress_ctx", _vp),
         ("skip_cb", SKIP_FN), ("skip_ctx", _vp),
         ("dict_cb", DICT_FN), ("dict_ctx", _vp),
+        ("submit", SUBMIT_FN), ("submit_ctx", _vp),
     ]
 
 

@@ -100,6 +100,16 @@ def init(device: int = 0) -> None:
     check(_lib.lib().plz4cu_init(device), "plz4cu_init")
 
 
+def init_devices(devices: Sequence[int]) -> None:
+    """Register the GPUs one stream may spread its batches over (NewWriter / NewReader with n_devices > 1 or -1)."""
+    arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+    check(_lib.lib().plz4cu_init_devices(len(devices), arr), "plz4cu_init_devices")
+
+
+def device_count() -> int:
+    return int(_lib.lib().plz4cu_device_count())
+
+
 def compress_block_bound(n: int) -> int:
     """plz4.CompressBlockBound (plz4_block.go:78-80)."""
     return int(_lib.lib().plz4cu_compress_bound(n))

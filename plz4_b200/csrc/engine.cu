@@ -115,7 +115,7 @@ struct HostBuf {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocPortable);
         if (e == cudaSuccess) cap = n;
         return e;
     }
@@ -210,6 +210,15 @@ struct plz4cu_dict {
     }
 };
 
+// devices one stream may spread over (plz4cu_init_devices); read by host_stream.cu
+static std::mutex g_devs_mu;
+static std::vector<int> g_devs;
+std::vector<int> plz4cu_internal_devices()
+{
+    std::lock_guard<std::mutex> lk(g_devs_mu);
+    return g_devs;
+}
+
 extern "C" {
 
 int plz4cu_device_count(void)
@@ -228,6 +237,33 @@ int plz4cu_init(int device)
     CU(cudaSetDevice(device));
     CU(cudaFree(0));
     return ensure_configured();
+}
+
+int plz4cu_init_devices(int ndev, const int* devs)
+{
+    int n = plz4cu_device_count();
+    if (n < 0) return n;
+    if (ndev <= 0 || !devs) return fail(PLZ4CU_ERR_ARG, "plz4cu_init_devices: no devices given");
+    std::vector<int> v;
+    for (int i = 0; i < ndev; i++) {
+        if (devs[i] < 0 || devs[i] >= n) return fail(PLZ4CU_ERR_ARG, "plz4cu_init_devices: device out of range");
+        if (std::find(v.begin(), v.end(), devs[i]) != v.end()) return fail(PLZ4CU_ERR_ARG, "plz4cu_init_devices: device listed twice");
+        v.push_back(devs[i]);
+    }
+    for (int d : v) {
+        CU(cudaSetDevice(d));
+        CU(cudaFree(0));
+        if (int r = ensure_configured()) return r;
+    }
+    CU(cudaSetDevice(v[0]));
+    std::lock_guard<std::mutex> lk(g_devs_mu);
+    g_devs = v;
+    return 0;
+}
+int plz4cu_registered_devices(void)
+{
+    std::lock_guard<std::mutex> lk(g_devs_mu);
+    return (int)g_devs.size();
 }
 
 const char* plz4cu_last_error(void) { return g_err.c_str(); }
@@ -258,10 +294,10 @@ void* plz4cu_host_alloc(size_t n)
         }
     }
     void* p = nullptr;
-    cudaError_t e = cudaHostAlloc(&p, cls, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&p, cls, cudaHostAllocPortable);
     if (e != cudaSuccess) {
         plz4cu_host_trim();                      // give cached slabs back and retry once
-        e = cudaHostAlloc(&p, cls, cudaHostAllocDefault);
+        e = cudaHostAlloc(&p, cls, cudaHostAllocPortable);
     }
     if (e != cudaSuccess) { fail(PLZ4CU_ERR_NOMEM, "cudaHostAlloc", e); return nullptr; }
     {

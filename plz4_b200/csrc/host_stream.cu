@@ -26,11 +26,14 @@
 #include <deque>
 #include <functional>
 #include <future>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <new>
 #include <vector>
+
+std::vector<int> plz4cu_internal_devices();            // engine.cu: what plz4cu_init_devices registered
 
 namespace {
 
@@ -46,13 +49,16 @@ class SerialExec {
     std::condition_variable cv_work, cv_done;
     std::deque<std::function<void()>> q;
     uint64_t submitted = 0, completed = 0;
-    bool stop = false;
+    bool stop = false, started = false, finished = false;
+    plz4cu_submit_fn spawn = nullptr;                 // WithWorkerPool: who runs this stage's loop (opts/opts.go:43-45)
+    void* spawn_ctx = nullptr;
+    static void entry(void* self) { static_cast<SerialExec*>(self)->run(); }
     void run()
     {
         std::unique_lock<std::mutex> lk(mu);
         for (;;) {
             cv_work.wait(lk, [&] { return stop || !q.empty(); });
-            if (q.empty()) return;
+            if (q.empty()) break;
             std::function<void()> f = std::move(q.front());
             q.pop_front();
             lk.unlock();
@@ -61,6 +67,8 @@ class SerialExec {
             completed++;
             cv_done.notify_all();
         }
+        finished = true;
+        cv_done.notify_all();
     }
 public:
     ~SerialExec()
@@ -72,11 +80,20 @@ public:
         }
         cv_work.notify_all();
         if (th.joinable()) th.join();
+        else if (started) {                               // the loop runs on a worker of the caller's pool: wait for it to leave
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&] { return finished; });
+        }
     }
+    void use_pool(plz4cu_submit_fn f, void* ctx) { spawn = f; spawn_ctx = ctx; }
     uint64_t submit(std::function<void()> f)               // returns the ticket to wait() on
     {
         std::lock_guard<std::mutex> lk(mu);
-        if (!th.joinable()) th = std::thread([this] { run(); });
+        if (!started) {
+            started = true;
+            // the reference hands its loops to opts.WorkerPool.Submit (async/writer.go:439-467); its stub is `go task()`
+            if (!spawn || spawn(spawn_ctx, &SerialExec::entry, this) != 0) th = std::thread([this] { run(); });
+        }
         q.push_back(std::move(f));
         cv_work.notify_one();
         return ++submitted;
@@ -214,6 +231,36 @@ void bulk_copy_mt(void* dst, const void* src, size_t n, int site = 0)
     static const bool check = getenv("PLZ4CU_COPY_CHECK") != nullptr;
     if (check && memcmp(dst, src, n) != 0) { fprintf(stderr, "bulk_copy_mt: MISMATCH n=%zu site=%d\n", n, site); abort(); }
     if (check) fprintf(stderr, "bulk_copy_mt ok n=%zu site=%d parts=%zu\n", n, site, parts);
+}
+
+// The devices a stream spreads its batches over (opts.n_devices): whole runs of independent blocks per
+// device, each through its own engine pipeline, no exchange between devices.
+std::vector<int> stream_devices(int n_devices, int fallback)
+{
+    std::vector<int> reg = plz4cu_internal_devices();
+    if (n_devices == 0 || n_devices == 1 || reg.size() < 2) return {fallback};
+    if (n_devices > 0 && (size_t)n_devices < reg.size()) reg.resize((size_t)n_devices);
+    return reg;
+}
+
+// run fn(part, first_block, block_count) for `parts` contiguous runs of nblk blocks, all at once, first error wins
+template <typename F>
+int for_each_part(uint32_t nblk, size_t parts, F fn)
+{
+    parts = std::min<size_t>(parts, std::max<uint32_t>(nblk, 1));
+    if (parts <= 1) return fn(0, 0u, nblk);
+    std::vector<std::future<int>> fut;
+    uint32_t b0 = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> runs;
+    for (size_t i = 0; i < parts; i++) {
+        const uint32_t b1 = (uint32_t)(((uint64_t)nblk * (i + 1)) / parts);
+        runs.emplace_back(b0, b1 - b0);
+        b0 = b1;
+    }
+    for (size_t i = 1; i < parts; i++) fut.push_back(std::async(std::launch::async, [&, i] { return fn(i, runs[i].first, runs[i].second); }));
+    int rc = fn(0, runs[0].first, runs[0].second);
+    for (auto& f : fut) { const int r = f.get(); if (rc >= 0 && r < 0) rc = r; }
+    return rc;
 }
 
 int current_device()
@@ -394,7 +441,8 @@ struct plz4cu_writer {
     std::atomic<int> state{0};                        // sticky error (first error wins, async/writer.go:553-555)
     int64_t src_mark = 0, dst_mark = 0;               // sink stage only
     XXH32 hasher;                                     // hash thread only (caller thread when synchronous)
-    plz4cu_dict_t* dict = nullptr;
+    std::vector<int> devs;                            // devices the batches are spread over (one unless opts.n_devices says so)
+    std::vector<plz4cu_dict_t*> dicts;                // the dictionary on each of them (nullptr: none)
     // staging: pageable while the stream is small, then two pinned slabs of one batch each — the caller fills one
     // while the engine thread works on the other (the reference's blocks-in-flight window, opts/opts.go:62-95)
     std::vector<uint8_t> small;
@@ -417,10 +465,17 @@ struct plz4cu_writer {
         bsz = block_size_of(opt.o.block_size_idx);
         batch = opt.batch_bytes(bsz, false);
         if (opt.o.level != 1 || opt.o.block_linked) state = PLZ4CU_Z_UNSUPPORTED;
+        devs = stream_devices(opt.o.n_devices, device);
+        dicts.assign(devs.size(), nullptr);
         if (!opt.dict.empty() && state == 0) {
-            dict = plz4cu_dict_create(opt.dict.data(), opt.dict.size());
-            if (!dict) state = PLZ4CU_Z_ENGINE;
+            for (size_t i = 0; i < devs.size() && state == 0; i++) {         // the dictionary lives on every device the stream uses
+                cudaSetDevice(devs[i]);
+                dicts[i] = plz4cu_dict_create(opt.dict.data(), opt.dict.size());
+                if (!dicts[i]) state = PLZ4CU_Z_ENGINE;
+            }
+            cudaSetDevice(device);
         }
+        if (opt.o.submit) { engine_q.use_pool(opt.o.submit, opt.o.submit_ctx); sink_q.use_pool(opt.o.submit, opt.o.submit_ctx); hash_q.use_pool(opt.o.submit, opt.o.submit_ctx); }
     }
     ~plz4cu_writer()
     {
@@ -428,7 +483,7 @@ struct plz4cu_writer {
         sink_q.drain();
         hash_q.drain();
         for (Slab& s : slabs) if (s.p) plz4cu_host_free(s.p);
-        if (dict) plz4cu_dict_destroy(dict);
+        for (plz4cu_dict_t* d : dicts) if (d) plz4cu_dict_destroy(d);
     }
     int report() { int s = state; if (s) reported = true; return s; }
     void set_error(int e) { int expect = 0; state.compare_exchange_strong(expect, e); }
@@ -464,7 +519,42 @@ struct plz4cu_writer {
         pk_cur ^= 1;
         if (threaded) sink_q.wait(pk.sink_ticket);
         if (!pk.buf.reserve(packed_cap)) return PLZ4CU_Z_ENGINE;
-        int rc = plz4cu_compress_batch_host(data, offs.data(), lens.data(), nblk, (uint32_t)bsz, opt.o.block_checksum, 0, dict,
+        if (devs.size() > 1 && nblk >= 2 * devs.size()) {
+            // several devices: contiguous runs of blocks, one per device, each through its own pipeline and into its own
+            // stretch of the packed buffer; the sink then writes the runs in order (the bytes are those of one device)
+            struct Run { uint32_t b0, nb; std::vector<uint64_t> off, poff; std::vector<uint32_t> len; };
+            auto runs = std::make_shared<std::vector<Run>>(devs.size());
+            const int rc = for_each_part(nblk, devs.size(), [&](size_t i, uint32_t b0, uint32_t nb) -> int {
+                Run& r = (*runs)[i];
+                r.b0 = b0; r.nb = nb;
+                if (nb == 0) return 0;
+                cudaSetDevice(devs[i]);
+                r.off.resize(nb); r.len.resize(nb); r.poff.resize(nb + 1);
+                for (uint32_t j = 0; j < nb; j++) { r.off[j] = (uint64_t)j * bsz; r.len[j] = lens[b0 + j]; }
+                return plz4cu_compress_batch_host(data + (size_t)b0 * bsz, r.off.data(), r.len.data(), nb, (uint32_t)bsz, opt.o.block_checksum, 0,
+                                                  dicts[i], pk.buf.p + (size_t)b0 * (bsz + 8), (size_t)nb * (bsz + 8), r.poff.data());
+            });
+            cudaSetDevice(device);
+            if (rc < 0) return PLZ4CU_Z_ENGINE;
+            const uint8_t* base = pk.buf.p;
+            auto deliver_runs = [this, base, runs, n]() -> int {
+                for (const Run& r : *runs) {
+                    if (r.nb == 0) continue;
+                    const size_t bytes = std::min<size_t>((size_t)r.nb * bsz, n - (size_t)r.b0 * bsz);
+                    std::vector<uint64_t> jp = r.poff;
+                    if (!opt.o.progress) jp.assign({0, r.poff[r.nb]});
+                    if (int e = deliver(base + (size_t)r.b0 * (bsz + 8), bytes, r.len, jp)) return e;
+                }
+                return 0;
+            };
+            if (!threaded) return deliver_runs();
+            pk.sink_ticket = sink_q.submit([this, deliver_runs] {
+                if (state) return;
+                if (int e = deliver_runs()) set_error(e);
+            });
+            return 0;
+        }
+        int rc = plz4cu_compress_batch_host(data, offs.data(), lens.data(), nblk, (uint32_t)bsz, opt.o.block_checksum, 0, dicts[0],
                                             pk.buf.p, packed_cap, poff.data());
         if (rc < 0) return PLZ4CU_Z_ENGINE;
         if (!threaded) return deliver(pk.buf.p, n, lens, poff);
@@ -670,7 +760,8 @@ struct plz4cu_reader {
     int64_t src_pos = 0, dst_pos = 0;
     int64_t read_offset;
     bool skip_content_size;
-    plz4cu_dict_t* dict = nullptr;
+    std::vector<int> devs;                            // devices the batches are spread over
+    std::vector<plz4cu_dict_t*> dicts;                // the frame's dictionary on each of them (empty: none yet)
     std::vector<uint8_t> cur_dict;
 
     // current frame
@@ -726,11 +817,21 @@ struct plz4cu_reader {
         read_offset = opt.o.read_offset;
         skip_content_size = !opt.o.content_size_check;
         cur_dict = opt.dict;
+        devs = stream_devices(opt.o.n_devices, device);
+        if (opt.o.submit) {
+            source_q.use_pool(opt.o.submit, opt.o.submit_ctx); hash_q.use_pool(opt.o.submit, opt.o.submit_ctx);
+            for (SerialExec& e : engine_q) e.use_pool(opt.o.submit, opt.o.submit_ctx);
+        }
+    }
+    void drop_dicts()
+    {
+        for (plz4cu_dict_t* d : dicts) if (d) plz4cu_dict_destroy(d);
+        dicts.clear();
     }
     ~plz4cu_reader()
     {
         quiesce();
-        if (dict) plz4cu_dict_destroy(dict);
+        drop_dicts();
     }
     void quiesce()
     {
@@ -824,7 +925,7 @@ struct plz4cu_reader {
             if ((flags & 0x01) && opt.o.dict_cb) {       // rdr/rdr.go:254-259
                 const void* dp = nullptr; size_t dl = 0;
                 if (opt.o.dict_cb(opt.o.dict_ctx, did, &dp, &dl) != 0) return PLZ4CU_Z_HEADER_READ;
-                if (dp) { cur_dict.assign(static_cast<const uint8_t*>(dp), static_cast<const uint8_t*>(dp) + dl); if (dict) { plz4cu_dict_destroy(dict); dict = nullptr; } }
+                if (dp) { cur_dict.assign(static_cast<const uint8_t*>(dp), static_cast<const uint8_t*>(dp) + dl); drop_dicts(); }
             }
             const bool independent = (flags & 0x20) != 0;
             bool check_hash = (flags & 0x04) != 0 && opt.o.content_checksum;
@@ -850,9 +951,13 @@ struct plz4cu_reader {
             }
             read_offset = 0;                            // applies to the first frame only
             if (!independent) return PLZ4CU_Z_UNSUPPORTED;   // linked frames are decoded on CPU cores by the reference
-            if (!cur_dict.empty() && !dict) {
-                dict = plz4cu_dict_create(cur_dict.data(), cur_dict.size());
-                if (!dict) return PLZ4CU_Z_ENGINE;
+            if (!cur_dict.empty() && dicts.empty()) {
+                for (int d : devs) {                                    // one copy per device the batches go to
+                    cudaSetDevice(d);
+                    dicts.push_back(plz4cu_dict_create(cur_dict.data(), cur_dict.size()));
+                    if (!dicts.back()) { cudaSetDevice(device); return PLZ4CU_Z_ENGINE; }
+                }
+                cudaSetDevice(device);
             }
             bsz = block_size_of((bd >> 4) & 7);
             blk_check = (flags & 0x10) != 0;
@@ -969,8 +1074,16 @@ struct plz4cu_reader {
         if (b.nblk == 0) return;
         b.out_len.resize(b.nblk);
         int rc = b.out.reserve((size_t)b.nblk * bsz) ? 0 : -1;
-        if (rc == 0) rc = plz4cu_decompress_batch_host(b.recs.p, b.recs_len, b.rec_off.data(), nullptr, b.nblk, (uint32_t)bsz, blk_check, 0,
-                                                       dict, b.out.p, (uint64_t)bsz, b.out_len.data());
+        // several devices: contiguous runs of the batch's blocks, one per device; every block has its own output slot, so
+        // the runs need no joining
+        const size_t parts = (devs.size() > 1 && b.nblk >= 2 * devs.size()) ? devs.size() : 1;
+        if (rc == 0) rc = for_each_part(b.nblk, parts, [&](size_t i, uint32_t b0, uint32_t nb) -> int {
+            if (nb == 0) return 0;
+            cudaSetDevice(devs[parts > 1 ? i : 0]);
+            plz4cu_dict_t* d = dicts.empty() ? nullptr : dicts[parts > 1 ? i : 0];
+            return plz4cu_decompress_batch_host(b.recs.p, b.recs_len, b.rec_off.data() + b0, nullptr, nb, (uint32_t)bsz, blk_check, 0,
+                                                d, b.out.p + (size_t)b0 * bsz, (uint64_t)bsz, b.out_len.data() + b0);
+        });
         if (rc < 0) { b.nblk = 0; b.tail_event = PLZ4CU_Z_ENGINE; }
     }
     // the serial checksum of the decoded bytes, in stream order, stops at the first block that failed; submitted by the

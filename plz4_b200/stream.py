@@ -37,7 +37,7 @@ class StreamError(Lz4Error):
 
 def _opts(*, level=1, parallel=1, pending_size=0, block_size_idx=7, block_checksum=False, content_checksum=True,
           block_linked=False, content_size=None, dict_id=None, dictionary=None, read_offset=0,
-          content_size_check=True, progress=None, skip_callback=None, dict_callback=None):
+          content_size_check=True, progress=None, skip_callback=None, dict_callback=None, n_devices=0, worker_pool=None):
     """Build a plz4cu_opts_t from With* style keyword options; returns (struct, keepalive list)."""
     o = _lib.Opts()
     _lib.lib().plz4cu_opts_default(C.byref(o))
@@ -55,6 +55,17 @@ def _opts(*, level=1, parallel=1, pending_size=0, block_size_idx=7, block_checks
         o.dict, o.dict_len = C.cast(buf, C.c_void_p), len(dictionary)
     o.read_offset = read_offset
     o.content_size_check = int(content_size_check)
+    o.n_devices = int(n_devices)                # WithParallel across GPUs: devices registered by init_devices() (-1: all)
+    if worker_pool is not None:                 # WithWorkerPool (plz4_opts.go:107): an object with submit(callable)
+        def _submit(_ctx, task, arg):
+            try:
+                worker_pool.submit(lambda: task(arg))
+                return 0
+            except Exception:
+                return -1
+        cb = _lib.SUBMIT_FN(_submit)
+        keep.append(cb)
+        o.submit = cb
     if progress:
         cb = _lib.PROGRESS_FN(lambda _ctx, s, d: progress(s, d))
         keep.append(cb)

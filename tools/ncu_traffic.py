@@ -13,6 +13,8 @@ for rep in reps:
     for r in rows[2:]:
         d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
         name = d["Kernel Name"].split("(")[0].split("<")[0].replace("void ", "").strip()
+        if "nan" in d["dram__bytes_read.sum"].lower() or "nan" in d["dram__bytes_write.sum"].lower():
+            continue                      # a pass that lost its DRAM counters: capture that kernel again
         rd = float(d["dram__bytes_read.sum"]) * SCALE[u["dram__bytes_read.sum"]]
         wr = float(d["dram__bytes_write.sum"]) * SCALE[u["dram__bytes_write.sum"]]
         res[name] = {"traffic": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr),
