@@ -487,6 +487,7 @@ lz4_stitch_kernel(FragArgs a)
     const uint32_t b = blockIdx.x;
     const uint8_t* src = a.e.src_base + a.e.src_off[b];
     const int n_blk = (int)a.e.src_len[b];
+    if (a.e.split_by_size && n_blk <= 65536) return;          // encoded whole by the CTA kernel
     uint8_t* rec = a.e.rec_base + (uint64_t)b * a.e.rec_stride;
     uint8_t* out = a.e.raw_blocks ? rec : rec + 4;
     const int cap = (int)a.e.dst_cap;
@@ -627,9 +628,9 @@ cudaError_t launch_dict_build(const uint8_t* dict, uint32_t dict_size, int bits,
     return cudaGetLastError();
 }
 
-static int g_span_want = 0;       // spans per block, 0 = by the number of blocks; PLZ4CU_SPAN_WANT (experiments)
+static int g_span_want = 0;       // fragments per span, 0 = sixteen; PLZ4CU_SPAN_WANT (experiments)
 static int g_spans = 1;           // blocks above 64 KiB: spans of fragments on the CTA encoder (0: one warp per 128 KiB fragment); PLZ4CU_SPANS
-static int g_cta_min = 8192;      // blocks at least this long get a CTA each (compress_cta.cu); PLZ4CU_CTA_MIN, 0 = never
+static int g_cta_min = 1;         // 0: the one-warp-per-block kernels of round 1 for everything (PLZ4CU_CTA_MIN=0, measurements)
 static int g_hash_bits = 12;     // 7 KiB of table per warp: 28 resident warps per SM against 12 with liblz4's 13 bits;
                                  // the one-step lazy parse more than pays the ratio back (profiles/r01_sweep.txt)
 
@@ -705,20 +706,23 @@ cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
 {
     if (a.nblk == 0) return cudaSuccess;
     const uint32_t max_len = a.max_src_len ? a.max_src_len : a.dst_cap;
-    if (a.dict_size == 0 && max_len <= 65536u && g_cta_min > 0 && max_len >= (uint32_t)g_cta_min)
-        return launch_compress_cta(a, stream);
-    // fragments are sized from the data, not from the room: the caller may offer less room than a block is long
-    // (plz4_block.go:100-109 WithBlockDst; the block then compresses into it or is refused, lz4.c:1382)
+    // No dictionary: a block of up to 64 KiB is the CTA kernel's, a larger one the span kernel's, whatever else the
+    // launch holds — so a block compresses to the same bytes in any batch, stream or device (tests/test_gpu_multi.py).
+    if (a.dict_size == 0 && max_len <= 65536u && g_cta_min > 0) return launch_compress_cta(a, stream);
     if (max_len > 65536u && a.dict_size == 0 && g_spans) {
-        // large blocks: spans of 64 KiB fragments, one CTA each (compress_cta.cu), then the stitch; a block is cut into
-        // several spans only as far as it takes to give every SM a CTA
+        // large blocks: spans of sixteen 64 KiB fragments, one CTA each (compress_cta.cu), then the stitch.  The cut does
+        // not depend on how many blocks the launch has: a block compresses to the same bytes whatever batch, stream or
+        // device it travels in (a 4 MiB block is four spans, so 64 of them — a 256 MiB file — already give every SM a CTA)
         const uint32_t nfrag = (max_len + 65535u) / 65536u;
-        uint32_t want = std::min<uint32_t>(nfrag, std::max<uint32_t>(1u, (222u + a.nblk - 1) / a.nblk));
-        if (g_span_want > 0) want = std::min<uint32_t>(nfrag, (uint32_t)g_span_want);
-        want = std::min<uint32_t>(want, (uint32_t)kMaxFrags);
-        const uint32_t span_frags = (nfrag + want - 1) / want;
+        uint32_t span_frags = g_span_want > 0 ? (uint32_t)g_span_want : 16u;
+        while ((nfrag + span_frags - 1) / span_frags > (uint32_t)kMaxFrags) span_frags *= 2;
         FragArgs fa{};
         fa.e = a;
+        fa.e.split_by_size = 1;
+        if (a.min_src_len <= 65536u) {                       // some block may be small (or nobody knows): those first
+            cudaError_t e0 = launch_compress_cta(fa.e, stream);
+            if (e0 != cudaSuccess) return e0;
+        }
         fa.frags_per_block = (nfrag + span_frags - 1) / span_frags;
         fa.frag_bytes = span_frags * 65536u;
         fa.frag_stride = (uint32_t)(((uint64_t)fa.frag_bytes + fa.frag_bytes / 255 + 16 + 15) & ~15ull);
@@ -729,7 +733,7 @@ cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
         fa.tmp = static_cast<uint8_t*>(scratch);
         fa.frag_len = reinterpret_cast<int32_t*>(fa.tmp + nspan * fa.frag_stride);
         fa.frag_tail = reinterpret_cast<uint32_t*>(fa.frag_len + nspan);
-        e = launch_compress_spans(a, fa.tmp, fa.frag_stride, fa.frags_per_block, fa.frag_bytes, fa.frag_len, fa.frag_tail, stream);
+        e = launch_compress_spans(fa.e, fa.tmp, fa.frag_stride, fa.frags_per_block, fa.frag_bytes, fa.frag_len, fa.frag_tail, stream);
         if (e == cudaSuccess) {
             lz4_stitch_kernel<<<a.nblk, kStitchWarps * 32, 0, stream>>>(fa);
             e = cudaGetLastError();

@@ -389,11 +389,9 @@ __device__ __forceinline__ void run_worker(SM& S, const TileEnv& C, int pw, int 
                     // 16-bit arithmetic: a group never straddles a multiple of 65536
                     const uint32_t g16 = (uint32_t)(tile_base + 32 * (gb + j)) & 0xFFFFu;
                     const uint32_t hw = __shfl_sync(FULL_MASK, h[j], (int)(w[j] & 31u));
-                    // An even position below this one, in this group, hashed like it: then its lane stored into this very
-                    // slot a moment ago, so what was read is this group's (never what an earlier tile or an earlier CTA
-                    // left in the scratch, which would make the choice of candidate depend on history).
-                    if (w[j] >= g16 && w[j] < g16 + (uint32_t)lane && (w[j] & 1u) == 0 && hw == h[j] &&
-                        tile_base + 32 * (gb + j) + (int)(w[j] & 31u) < hash_end) {
+                    // (the scratch is cleared when the CTA starts, so what is read here was written by this worker while it
+                    // worked on this block: the choice of candidate never depends on what ran on the SM before)
+                    if (w[j] >= g16 && w[j] < g16 + (uint32_t)lane && hw == h[j]) {
                         c[j] = w[j];
                         pg[j * kPvStride] = (uint16_t)w[j];
                     }
@@ -620,6 +618,7 @@ lz4_compress_cta_kernel(EncodeArgs a)
     uint8_t* rec = a.rec_base + (uint64_t)b * a.rec_stride;
     uint8_t* payload = a.raw_blocks ? rec : rec + 4;
     const int cap = (int)a.dst_cap;
+    if (a.split_by_size && n_in > 65536) return;              // the span kernel's block
     // a block this kernel cannot hold is stored / refused (launch_compress never sends one: see kernels.h)
     const bool oversize = n_in > 65536;
     const int n = oversize ? 0 : n_in;
@@ -644,6 +643,8 @@ lz4_compress_cta_kernel(EncodeArgs a)
         uint4* t4 = reinterpret_cast<uint4*>(S.table);
         const uint4 fill = make_uint4(~0u, ~0u, ~0u, ~0u);       // -1 everywhere
         for (int i = tid; i < (int)(sizeof(S.table) / 16); i += kCtaThreads) t4[i] = fill;
+        uint4* r4 = reinterpret_cast<uint4*>(S.recs);            // the workers' scratch tables start empty (see run_worker (2))
+        for (int i = tid; i < (int)(sizeof(S.recs) / 16); i += kCtaThreads) r4[i] = fill;
         // what the bulk copy does not bring: the last n & 15 bytes (or everything, from an unaligned source), zero padding
         if (aligned) {
             for (int k = (int)bulk + tid; k < n; k += kCtaThreads) S.win[k] = src[k];
@@ -786,6 +787,7 @@ lz4_compress_span_kernel(EncodeArgs a, uint8_t* tmp, uint32_t slot_stride, uint3
     if (b >= a.nblk) return;
     const uint8_t* src = a.src_base + a.src_off[b];
     const int n_blk = (int)a.src_len[b];
+    if (n_blk <= 65536) return;                                   // the CTA kernel's block
     const int span_start = (int)(sp * span_bytes);
     if (span_start >= n_blk && sp != 0) {
         if (tid == 0) span_len[w] = -2;                           // this span does not exist
@@ -805,6 +807,8 @@ lz4_compress_span_kernel(EncodeArgs a, uint8_t* tmp, uint32_t slot_stride, uint3
         uint4* t4 = reinterpret_cast<uint4*>(S.table);
         const uint4 fill = make_uint4(~0u, ~0u, ~0u, ~0u);
         for (int i = tid; i < (int)(sizeof(S.table) / 16); i += kSpanThreads) t4[i] = fill;
+        uint4* r4 = reinterpret_cast<uint4*>(S.recs);
+        for (int i = tid; i < (int)(sizeof(S.recs) / 16); i += kSpanThreads) r4[i] = fill;
     }
     uint8_t* cur = S.win + 65536;                                 // the current fragment; the one before it lies below
     int my_x = span_start;

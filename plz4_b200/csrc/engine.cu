@@ -666,7 +666,8 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
     uint8_t* hout = static_cast<uint8_t*>(packed);
     uint32_t max_len = 0;
     uint64_t total_len = 0;
-    for (uint32_t b = 0; b < nblk; b++) { max_len = std::max(max_len, src_len[b]); total_len += src_len[b]; }
+    uint32_t min_len = 0xFFFFFFFFu;
+    for (uint32_t b = 0; b < nblk; b++) { max_len = std::max(max_len, src_len[b]); min_len = std::min(min_len, src_len[b]); total_len += src_len[b]; }
     // a chunk is an eighth of the call, between kChunkMinBytes (16 MiB: a stream's 64 MiB batch still pipelines over the
     // lanes) and 64 MiB (a whole buffer is not cut finer than its copies need: every chunk costs two host waits)
     const uint64_t chunk_min = std::min<uint64_t>(std::max<uint64_t>(total_len / 8, kChunkMinBytes), std::max<uint64_t>(kChunkMinBytes, 64ull << 20));
@@ -711,7 +712,7 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         a.src_len = reinterpret_cast<const uint32_t*>(L.off.as<uint64_t>() + cnt);
         a.nblk = cnt; a.dst_cap = dst_cap; a.block_checksum = block_checksum; a.raw_blocks = raw_blocks;
         a.rec_base = L.out.as<uint8_t>(); a.rec_stride = stride; a.rec_len = L.res.as<uint32_t>();
-        a.max_src_len = max_len;
+        a.max_src_len = max_len; a.min_src_len = min_len;
         if (dict && dict->size) { a.dict = dict->d_bytes; a.dict_size = dict->size; a.dict_table = dict->table(compress_hash_bits(dst_cap)); }
         CU(launch_compress(a, L.st));
         CU(launch_pack(L.out.as<uint8_t>(), stride, L.res.as<uint32_t>(), cnt, L.packed.as<uint8_t>(), L.poff.as<uint64_t>(), L.st));

@@ -42,7 +42,10 @@ struct EncodeArgs {
     uint8_t* rec_base;
     uint32_t rec_stride;
     uint32_t* rec_len;
-    uint32_t max_src_len;         // upper bound of src_len[] (exact on the host paths); picks the kernel and the fragment count
+    uint32_t max_src_len;         // upper bound of src_len[] (exact on the host paths); picks the kernels and the span count
+    uint32_t min_src_len;         // lower bound of src_len[] (0 = unknown): spares the launch of a kernel no block needs
+    int split_by_size;            // set by launch_compress: blocks above 64 KiB belong to the span kernel, the rest to the CTA
+                                  // kernel, each kernel leaving the other's blocks alone (a block's bytes never depend on its batch)
 };
 cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream);
 // one CTA per block of <= 64 KiB, block staged in shared memory by TMA (compress_cta.cu); no dictionary

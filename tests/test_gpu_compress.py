@@ -169,3 +169,22 @@ def test_block_longer_than_the_room_offered(gpu, codec):
     c = gpu.compress_block(big)
     back, data = codec.decompress(c, len(big))
     assert back == len(big) and data == big
+
+
+def test_a_block_compresses_the_same_in_any_batch(gpu):
+    """Kernels are chosen per block (up to 64 KiB: one CTA; above: spans of sixteen fragments), never by what else the launch
+    holds: the bytes of a block do not depend on its batch — what lets several writers, batch sizes or GPUs produce one frame."""
+    sizes = [4 << 20, 30_000, 200_000, 65536, 10, 1 << 20, 65537, 0, 3_000_000]
+    blocks = [make("log", n, seed=40 + i) for i, n in enumerate(sizes)]
+    cap = gpu.compress_block_bound(max(sizes))
+    buf, off = b"".join(blocks), np.cumsum([0] + sizes)[:-1]
+    packed, poff = gpu.compress_batch(buf, off, sizes, cap, raw_blocks=True)
+    together = [packed[int(poff[i]): int(poff[i + 1])].tobytes() for i in range(len(sizes))]
+    for i, b in enumerate(blocks):
+        if not b:
+            continue
+        alone, p1 = gpu.compress_batch(b, [0], [len(b)], cap, raw_blocks=True)
+        assert alone[: int(p1[1])].tobytes() == together[i], (i, sizes[i])
+    # and in a batch of its own kind
+    same, p2 = gpu.compress_batch(blocks[3] * 3, [0, 65536, 131072], [65536] * 3, cap, raw_blocks=True)
+    assert same[: int(p2[1])].tobytes() == together[3]
