@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -262,6 +263,14 @@ int for_each_part(uint32_t nblk, size_t parts, F fn)
     for (auto& f : fut) { const int r = f.get(); if (rc >= 0 && r < 0) rc = r; }
     return rc;
 }
+
+// stage timing of a reader for tuning (PLZ4CU_STREAM_PROF=1): microseconds per stage, printed when the reader is freed
+struct StageClock {
+    std::atomic<int64_t> us[6];
+    StageClock() { for (auto& u : us) u = 0; }
+    static bool on() { static const bool v = getenv("PLZ4CU_STREAM_PROF") != nullptr; return v; }
+    static int64_t now() { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+};
 
 int current_device()
 {
@@ -832,6 +841,10 @@ struct plz4cu_reader {
     {
         quiesce();
         drop_dicts();
+        if (StageClock::on())
+            fprintf(stderr, "reader stages (ms): source read %.1f  decode (sum over engine threads) %.1f  caller waits for source %.1f + for decode %.1f  sink writes %.1f\n",
+                    clk.us[0] / 1e3, clk.us[1] / 1e3, clk.us[2] / 1e3, clk.us[4] / 1e3, clk.us[3] / 1e3);
+        if (StageClock::on()) fprintf(stderr, "  of the source read: %.1f ms inside %lld read callbacks\n", clk.us[5] / 1e3, (long long)rd_calls.load());
     }
     void quiesce()
     {
@@ -979,6 +992,8 @@ struct plz4cu_reader {
     // blk/frame.go:54-112 for up to `want_bytes` of blocks: the records of one batch, in order (source thread).
     // Bytes read past the last record of a batch while the body goes on (bulk reads, below); they open the next batch.
     std::vector<uint8_t> carry;
+    StageClock clk;                                   // 0 source read, 1 decode, 2 wait for a batch, 3 sink write
+    std::atomic<int64_t> rd_calls{0};
 
     void read_records(Batch& b, size_t want_bytes)
     {
@@ -1017,7 +1032,9 @@ struct plz4cu_reader {
                 }
                 const size_t piece = std::max<size_t>(upto - fill, std::min<size_t>(8u << 20, std::max<size_t>(64u << 10, b.recs.cap - fill)));
                 if (!room_for(fill + piece)) { eof = true; failed = true; break; }
+                const int64_t tr0 = StageClock::on() ? StageClock::now() : 0;
                 const int64_t r = rd(ctx, b.recs.p + fill, std::min(piece, b.recs.cap - fill));
+                if (StageClock::on()) { clk.us[5] += StageClock::now() - tr0; rd_calls++; }
                 if (r <= 0) { eof = true; failed = r < 0; break; }
                 fill += (size_t)r;
             }
@@ -1126,9 +1143,16 @@ struct plz4cu_reader {
             }
             Batch& b = bt[k % kSlots];
             if (b.hash_ticket) hash_q.wait(b.hash_ticket);      // the previous tenant of these buffers may still be hashed
+            const int64_t t0 = StageClock::on() ? StageClock::now() : 0;
             read_records(b, next_fill_bytes());
+            if (StageClock::on()) clk.us[0] += StageClock::now() - t0;
             const bool last = b.tail_event != 0;
-            if (b.nblk) b.ticket = engine_q[k % kSlots].submit([this, &b] { cudaSetDevice(device); decode_records(b); });
+            if (b.nblk) b.ticket = engine_q[k % kSlots].submit([this, &b] {
+                cudaSetDevice(device);
+                const int64_t t1 = StageClock::on() ? StageClock::now() : 0;
+                decode_records(b);
+                if (StageClock::on()) clk.us[1] += StageClock::now() - t1;
+            });
             {
                 std::lock_guard<std::mutex> lk(ring_mu);
                 produced = k + 1;
@@ -1169,11 +1193,15 @@ struct plz4cu_reader {
                 std::unique_lock<std::mutex> lk(ring_mu);
                 released = next;                                // everything before `next` may be overwritten
                 ring_cv.notify_all();
+                const int64_t t2 = StageClock::on() ? StageClock::now() : 0;
                 ring_cv.wait(lk, [&] { return produced > next || source_done; });
                 there = produced > next;
+                if (StageClock::on()) clk.us[2] += StageClock::now() - t2;
             }
             Batch& b = bt[next % kSlots];
+            const int64_t t3 = StageClock::on() ? StageClock::now() : 0;
             if (there) engine_q[next % kSlots].wait(b.ticket);
+            if (StageClock::on()) clk.us[4] += StageClock::now() - t3;
             else { b.nblk = 0; b.tail_event = PLZ4CU_Z_ENGINE; }         // the source loop stopped short: cannot happen while reading
         }
         cb_index = next;
@@ -1284,7 +1312,9 @@ struct plz4cu_reader {
             int err = 0;
             for (;;) {
                 if (have_block && cur_off < cur_len) {
+                    const int64_t t4 = StageClock::on() ? StageClock::now() : 0;
                     int64_t k = w(wctx, block_ptr() + cur_off, cur_len - cur_off);
+                    if (StageClock::on()) clk.us[3] += StageClock::now() - t4;
                     if (k > 0) { cur_off += (size_t)k; sum += k; }
                     if (k < 0 || cur_off < cur_len) { err = PLZ4CU_Z_WRITE; break; }
                 }
