@@ -46,8 +46,8 @@ __device__ unsigned long long g_cta_prof[16];
 
 namespace {
 
-constexpr int kCtaThreads = 320;
-constexpr int kWorkers = 9;                     // warps 0..8; warp 9 hashes
+constexpr int kCtaThreads = 384;
+constexpr int kWorkers = 11;                    // warps 0..8; warp 9 hashes
 constexpr int kTile = 1024;                     // positions per tile: 32 lanes x 32 positions
 constexpr int kMaxTiles = 64;
 constexpr int kPvStride = 34;                   // u16 per group in prev[]: 17 words, so lanes reading their own group hit 32 banks
@@ -58,7 +58,7 @@ constexpr int kLongLit = 48;                    // literal runs from this length
 constexpr int kWinPad = 32;
 constexpr int kHashChunk = 512;                 // bytes the hasher consumes per step (32 stripes)
 
-constexpr int kSpanWorkers = 20;                // large blocks: one CTA per SM, every warp a worker
+constexpr int kSpanWorkers = 22;                // large blocks: one CTA per SM, every warp a worker
 constexpr int kSpanThreads = kSpanWorkers * 32;
 
 template <int kWin, int kNW>

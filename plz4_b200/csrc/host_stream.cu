@@ -565,7 +565,7 @@ struct plz4cu_writer {
         }
         int rc = plz4cu_compress_batch_host(data, offs.data(), lens.data(), nblk, (uint32_t)bsz, opt.o.block_checksum, 0, dicts[0],
                                             pk.buf.p, packed_cap, poff.data());
-        if (rc < 0) return PLZ4CU_Z_ENGINE;
+        if (rc < 0) { if (getenv("PLZ4CU_DEBUG")) fprintf(stderr, "writer: engine call failed (%d): %s\n", rc, plz4cu_last_error()); return PLZ4CU_Z_ENGINE; }
         if (!threaded) return deliver(pk.buf.p, n, lens, poff);
         // the sink job owns copies of the per-block tables only when somebody watches block boundaries
         std::vector<uint32_t> jl;
@@ -844,7 +844,7 @@ struct plz4cu_reader {
         if (StageClock::on())
             fprintf(stderr, "reader stages (ms): source read %.1f  decode (sum over engine threads) %.1f  caller waits for source %.1f + for decode %.1f  sink writes %.1f\n",
                     clk.us[0] / 1e3, clk.us[1] / 1e3, clk.us[2] / 1e3, clk.us[4] / 1e3, clk.us[3] / 1e3);
-        if (StageClock::on()) fprintf(stderr, "  of the source read: %.1f ms inside %lld read callbacks\n", clk.us[5] / 1e3, (long long)rd_calls.load());
+        if (StageClock::on()) fprintf(stderr, "  of the source read: %.1f ms inside %lld read callbacks, %.1f ms in %lld growths of the record area\n", clk.us[5] / 1e3, (long long)rd_calls.load(), grow_us.load() / 1e3, (long long)grows.load());
     }
     void quiesce()
     {
@@ -993,7 +993,7 @@ struct plz4cu_reader {
     // Bytes read past the last record of a batch while the body goes on (bulk reads, below); they open the next batch.
     std::vector<uint8_t> carry;
     StageClock clk;                                   // 0 source read, 1 decode, 2 wait for a batch, 3 sink write
-    std::atomic<int64_t> rd_calls{0};
+    std::atomic<int64_t> rd_calls{0}, grow_us{0}, grows{0};
 
     void read_records(Batch& b, size_t want_bytes)
     {
@@ -1012,7 +1012,10 @@ struct plz4cu_reader {
         bool eof = false, failed = false;
         auto room_for = [&](size_t upto) -> bool {
             if (upto <= b.recs.cap) return true;
-            return b.recs.grow(std::min(cap_max, std::max(upto, 2 * b.recs.cap)), fill);
+            const int64_t tg = StageClock::on() ? StageClock::now() : 0;
+            const bool ok = b.recs.grow(std::min(cap_max, std::max(upto, 2 * b.recs.cap)), fill);
+            if (StageClock::on()) { grow_us += StageClock::now() - tg; grows++; }
+            return ok;
         };
         if (bulk && !carry.empty()) {
             if (!room_for(carry.size())) { b.tail_event = PLZ4CU_Z_ENGINE; b.nblk = 0; return; }
@@ -1101,7 +1104,7 @@ struct plz4cu_reader {
             return plz4cu_decompress_batch_host(b.recs.p, b.recs_len, b.rec_off.data() + b0, nullptr, nb, (uint32_t)bsz, blk_check, 0,
                                                 d, b.out.p + (size_t)b0 * bsz, (uint64_t)bsz, b.out_len.data() + b0);
         });
-        if (rc < 0) { b.nblk = 0; b.tail_event = PLZ4CU_Z_ENGINE; }
+        if (rc < 0) { if (getenv("PLZ4CU_DEBUG")) fprintf(stderr, "reader: engine call failed (%d): %s\n", rc, plz4cu_last_error()); b.nblk = 0; b.tail_event = PLZ4CU_Z_ENGINE; }
     }
     // the serial checksum of the decoded bytes, in stream order, stops at the first block that failed; submitted by the
     // caller's thread when it starts on the batch, so the jobs line up in batch order whatever order decodes finish in
@@ -1201,8 +1204,8 @@ struct plz4cu_reader {
             Batch& b = bt[next % kSlots];
             const int64_t t3 = StageClock::on() ? StageClock::now() : 0;
             if (there) engine_q[next % kSlots].wait(b.ticket);
-            if (StageClock::on()) clk.us[4] += StageClock::now() - t3;
             else { b.nblk = 0; b.tail_event = PLZ4CU_Z_ENGINE; }         // the source loop stopped short: cannot happen while reading
+            if (StageClock::on()) clk.us[4] += StageClock::now() - t3;
         }
         cb_index = next;
         have_batch = true;

@@ -79,7 +79,7 @@ class _Pool:
 
     def submit(self, fn):
         self.tasks += 1
-        t = threading.Thread(target=fn, name=f"pool-{self.tasks}")
+        t = threading.Thread(target=fn, name=f"pool-{self.tasks}", daemon=True)
         self.threads.append(t)
         t.start()
 

@@ -26,7 +26,7 @@ rt = C.CDLL(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_
 def cudamemcpy(dst, src, n, kind=4):
     r = rt.cudaMemcpy(C.c_void_p(dst), C.c_void_p(src), C.c_size_t(n), kind); assert r == 0, r
 for kind in ["log", "words", "runs", "random", "zeros"]:
-    for n in [0, 1, 13, 63, 64, 100, 4096, 65535, 65536, 100000]:
+    for n in [0, 1, 13, 63, 64, 100, 4096, 65535, 65536, 100000, 300001, 2600000]:
         for misalign in [0, 1, 7]:
             data = np.frombuffer(make(kind, n), dtype=np.uint8)
             d_src = dev((n + misalign + 15) // 16 * 16 + 16 * PAD); 
