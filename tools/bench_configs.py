@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Secondary measurements: the BASELINE.json configs that are NOT the headline bench line, scaled to
 minutes, GPU engine next to the reference's liblz4 on all host cores.  Prints one JSON object.
-These are reported context (profiles/r01_configs.json), not bench.py lines."""
+These are reported context (profiles/r02_configs.json), not bench.py lines."""
 import ctypes as C, io, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -83,21 +83,44 @@ res["config0_256MiB_4MiB_blocks_bx_cx_streams"] = {
     "note": "NewWriter/NewReader over in-memory C endpoints, pageable caller buffers; CPU columns are block-level (no stream layer, no content checksum); "
             "decode of 4 MiB blocks is one CTA per block (64 blocks here): DESIGN.md 4.1b"}
 
-# ---- configs[2]: decode reference-produced frames (4 MiB blocks, bx) from random WithReadOffset starts
+# ---- configs[2]: decode reference-produced frames (4 MiB blocks, bx) from 64 random WithReadOffset starts into a 1 GiB frame,
+# 64 MiB read from every start; beside it the reference's liblz4 decoding the same blocks on all host cores
 from oracle import frame_oracle as F
-sub = raw[: 64 << 20]
+big1 = logtext(1 << 30, seed=0x1234)
+sub = big1.tobytes()
 marks = []
 rframe = F.write_frame(sub, F.Opts(block_idx=7, block_checksum=True, content_checksum=False), port, progress=lambda s, d: marks.append((s, d)))
 rng = np.random.default_rng(3)
-picks = [marks[i] for i in rng.integers(0, len(marks) - 1, size=4)]
-rf_np = np.frombuffer(rframe, dtype=np.uint8); ra_out = np.empty(len(sub), dtype=np.uint8)
+picks = [marks[i] for i in rng.integers(0, len(marks) - 17, size=64)]
+rf_np = np.frombuffer(rframe, dtype=np.uint8)
+want = 64 << 20
+ra_out = np.empty(want + (4 << 20), dtype=np.uint8)
+def c_read_some(frame_np, dst_np, nbytes, **opts):
+    o, keep = S._opts(**opts)
+    srcb = L.plz4cu_membuf_new(vp(frame_np), frame_np.size, frame_np.size)
+    r = L.plz4cu_reader_new(fn(L.plz4cu_membuf_read), fn(L.plz4cu_membuf_seek), srcb, C.byref(o))
+    got = 0
+    while got < nbytes:
+        k = L.plz4cu_reader_read(r, C.c_void_p(dst_np.ctypes.data + got), nbytes - got)
+        assert k >= 0, k
+        if k == 0:
+            break
+        got += k
+    L.plz4cu_reader_close(r); L.plz4cu_reader_free(r); L.plz4cu_membuf_free(srcb)
+    return got
+L.plz4cu_reader_read.restype = C.c_int64
+L.plz4cu_reader_read.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
 def ra():
     tot = 0
     for s_, d_ in picks:
-        tot += c_decompress(rf_np, rf_np.size, ra_out, read_offset=d_)
+        tot += c_read_some(rf_np, ra_out, want, read_offset=d_)
     return tot
 tot = ra(); t3 = best(ra, 2)
-res["config2_random_access_reference_frames_4MiB"] = {"starts": len(picks), "decoded_bytes": tot, "gpu_gbs": round(tot / t3 / 1e9, 2)}
+assert ra_out[:want].tobytes() == sub[picks[-1][0]: picks[-1][0] + want]
+_, cd2, _ = cpu_blocks(big1[: 256 << 20], 4 << 20)
+res["config2_random_access_reference_frames_4MiB"] = {"starts": len(picks), "frame_bytes": len(rframe), "read_per_start": want, "decoded_bytes": tot,
+                                                      "gpu_gbs": round(tot / t3 / 1e9, 2), "cpu_decompress_gbs_same_blocks_all_cores": round(cd2, 2),
+                                                      "note": "NewReader(WithReadOffset) over a reference-written 1 GiB frame, pageable buffers; the CPU column decodes 4 MiB blocks of the same text on all host cores (block level, no stream layer)"}
 
 # ---- configs[3]: 4 KiB payloads + 64 KiB dictionary, one batch call (device work + PCIe), vs liblz4 amortised dict ctx
 corpus = logtext(64 << 20, seed=13)
