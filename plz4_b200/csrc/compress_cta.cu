@@ -56,6 +56,10 @@ constexpr int kLaneCap = 64;                    // a lane extends a match this f
 constexpr int kLazyBelow = 16;                  // the lazy check is made for matches shorter than this
 constexpr int kLongLit = 48;                    // literal runs from this length on are copied by the whole warp
 constexpr int kWinPad = 32;
+#ifndef PLZ4CU_WAIT_NAP
+#define PLZ4CU_WAIT_NAP 64
+#endif
+constexpr unsigned kWaitNap = PLZ4CU_WAIT_NAP;     // ns between two polls of an mbarrier
 constexpr int kHashChunk = 512;                 // bytes the hasher consumes per step (32 stripes)
 
 constexpr int kSpanWorkers = 22;                // large blocks: one CTA per SM, every warp a worker
@@ -131,6 +135,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
             : "r"(a), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) return;
+        __nanosleep(kWaitNap);                                // a waiting warp leaves its issue slots to the workers
         if ((spins & 255u) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
 }
