@@ -344,8 +344,10 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
     }
 }
 
+// 48 warps per SM at 40 registers beat 32 warps at 64 despite ~140 bytes of spills (220 -> 232 GB/s): the kernel waits on
+// loads of match sources that miss L2, and more warps in flight hide more of them (measured at 8, 10, 12, 14, 16 CTAs per SM)
 template <bool kDict, bool kRing>
-__global__ void __launch_bounds__(kDecodeThreads)
+__global__ void __launch_bounds__(kDecodeThreads, kRing ? 1 : 12)
 lz4_decompress_kernel(DecodeArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn_smem[];              // kRing: 64 KiB per warp
