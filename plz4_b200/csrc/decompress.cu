@@ -134,6 +134,15 @@ __device__ __noinline__ int decode_one(const uint8_t* __restrict__ src, int n, u
 
 // ---------------------------------------------------------------- batched decode
 
+// a byte that this kernel may have written itself (match source) or not (literal): plain global load, never the read-only path
+// (predicated in place: a branch around one load costs more than the load)
+__device__ __forceinline__ uint32_t ld_global_u8_if(const uint8_t* p, bool need)
+{
+    uint32_t v = 0;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u8 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((uint32_t)need) : "memory");
+    return v;
+}
+
 // kRing: the last 64 KiB of output are mirrored in a shared-memory ring and match sources are read from there.
 // Used when a launch has too few blocks to hide global-memory latency with other warps (large block sizes):
 // the per-chunk round trip drops from an L2/HBM access to a shared-memory access.
@@ -143,16 +152,16 @@ struct HashAlong {
     bool on;
     uint32_t acc;
     int done;                  // payload bytes in acc (a multiple of 512)
-    const uint32_t* wp;        // word-aligned payload
-    uint32_t sh;               // its byte shift, in bits
 };
 
 // hash the whole 512-byte chunks below `upto` (kept out of line: the decode loop has no registers to lend)
-static __device__ __noinline__ void hash_along(HashAlong& H, int upto, int lane)
+static __device__ __noinline__ void hash_along(HashAlong& H, const uint8_t* payload, int upto, int lane)
 {
     const int nch = ((upto & ~511) - H.done) >> 9;
     if (nch > 0) {
-        H.acc = xxh32_consume_global<false>(H.acc, H.wp + (H.done >> 2), H.sh, nch, lane);
+        const uintptr_t pa = reinterpret_cast<uintptr_t>(payload);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(pa & ~uintptr_t(3));     // word-aligned payload and its shift
+        H.acc = xxh32_consume_global<false>(H.acc, wp + (H.done >> 2), (uint32_t)(pa & 3u) * 8u, nch, lane);
         H.done += nch << 9;
     }
 }
@@ -171,13 +180,12 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
     int ip = 0, op = 0;
     const bool check_offset = dsz < 65536;
     // word-aligned view of the compressed stream: byte q of src is byte (d4 + q) of src4
-    const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
-    const uint32_t* __restrict__ src4 = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
-    const uint32_t d4 = (uint32_t)sa & 3u;
+    const uint32_t d4 = (uint32_t)reinterpret_cast<uintptr_t>(src) & 3u;
+    const uint32_t* __restrict__ src4 = reinterpret_cast<const uint32_t*>(src - d4);
     const uint32_t last4 = (d4 + (uint32_t)n - 1u) >> 2;         // last word holding a valid byte
 
     for (;;) {
-        if (H.on && ip + 256 > H.done && H.done + 512 <= n) hash_along(H, min(ip + 1024, n), lane);
+        if (H.on && ip + 256 > H.done && H.done + 512 <= n) hash_along(H, src, min(ip + 1024, n), lane);
         // ---- 1. parse up to 32 shortcut sequences; lane k latches sequence k.
         // The next 128 compressed bytes sit in registers (one word per lane).  Every lane first computes, for
         // each of its own 4 bytes, how long a sequence header starting there would be (token + literals +
@@ -282,6 +290,8 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                 // ---- 3. copy: 32 output bytes per step, one per lane
                 const int out0 = op;
                 const int out1 = __shfl_sync(FULL_MASK, o + span, nseq - 1);
+                const int total = out1 - out0;
+                const int ip_next = __shfl_sync(FULL_MASK, my_ipn(), nseq - 1);
                 const int orel = mine ? o - out0 : 0x7FFFFFF;                 // sequences outside the batch start "never"
                 // bitmap of sequence starts over the batch's output range: lane j ends up with bits out0+32j .. out0+32j+31
                 bitmap[lane] = 0;
@@ -289,32 +299,47 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                 if (mine) atomicOr(&bitmap[orel >> 5], 1u << (orel & 31));
                 __syncwarp();
                 const uint32_t my_bits = bitmap[lane];
-                // everything a byte needs to know about its sequence, in two words
-                const uint32_t packA = (uint32_t)(orel & 0x3FF) | ((uint32_t)my_lit << 10) | (my_off << 16);
+                // what a byte needs to know about its sequence, in two words: where the match starts (relative to out0:
+                // bytes below it are literals) with the offset, and where its literals lie in the compressed block
+                // (literal for the byte at batch position x: src[litrel + x])
+                const uint32_t packA = (uint32_t)((orel + my_lit) & 0x7FF) | (my_off << 16);
+                const int litrel = my_litpos - orel;
+                const uint32_t lmask = (2u << lane) - 1u;
                 uint8_t* dx = dst + out0 + lane;
+                int kbase = -1;                                               // sequences that start below the chunk, minus one
                 int j = 0;
-                for (int c = 0; c < out1 - out0; c += 32, j++, dx += 32) {
+                for (int c = 0; c < total; c += 32, j++, dx += 32) {
                     const int xr = c + lane;                                                        // byte position relative to out0
                     // owner of the byte = last sequence starting at or before it
                     const uint32_t sbits = __shfl_sync(FULL_MASK, my_bits, j);
-                    const int k = __popc(__ballot_sync(FULL_MASK, orel < c)) - 1 + __popc(sbits & ((2u << lane) - 1u));
+                    const int k = kbase + __popc(sbits & lmask);
+                    kbase += __popc(sbits);
                     const uint32_t ka = __shfl_sync(FULL_MASK, packA, k);
-                    const int kp = __shfl_sync(FULL_MASK, my_litpos, k);
-                    const bool live = xr < out1 - out0;
-                    const int d = xr - (int)(ka & 0x3FFu);                                          // byte index inside the sequence
-                    const bool is_lit = d < (int)((ka >> 10) & 63u);
-                    const int sr = xr - (int)(ka >> 16);                                            // match source, relative to out0
-                    const bool fwd = live && !is_lit && sr >= c;                                    // source inside this chunk
+                    const int kp = __shfl_sync(FULL_MASK, litrel, k);
+                    const bool live = xr < total;
+                    const bool is_lit = xr < (int)(ka & 0x7FFu);
+                    const int off = (int)(ka >> 16);
+                    const bool fwd = live && !is_lit && off <= lane;                                // match source inside this chunk
                     uint32_t val = 0;
-                    if (live && !fwd) {
-                        const int s = out0 + sr;
-                        if (is_lit) val = src[kp + d];
-                        else if (kDict && s < 0) val = dict[dsz + s];
-                        else val = kRing ? ring[s & 0xFFFF] : dst[s];
+                    if (kRing) {
+                        if (live && !fwd) {
+                            const int s = out0 + xr - off;
+                            if (is_lit) val = src[kp + xr];
+                            else if (kDict && s < 0) val = dict[dsz + s];
+                            else val = ring[s & 0xFFFF];
+                        }
+                    } else {
+                        // one load from one pointer: the literal in the compressed block, or the match source `off` below me
+                        const uint8_t* p = is_lit ? src + (kp + xr) : static_cast<const uint8_t*>(dx) - off;
+                        if (kDict) {
+                            const int s = out0 + xr - off;
+                            if (!is_lit && s < 0) p = dict + (dsz + s);
+                        }
+                        val = ld_global_u8_if(p, live && !fwd);
                     }
                     if (__any_sync(FULL_MASK, fwd)) {
                         // forward values along in-chunk chains: root = the lane whose loaded value this byte finally equals
-                        int root = fwd ? (sr - c) : lane;
+                        int root = fwd ? lane - off : lane;
 #pragma unroll
                         for (int it = 0; it < 5; it++) root = __shfl_sync(FULL_MASK, root, root);
                         val = __shfl_sync(FULL_MASK, val, root);
@@ -325,7 +350,7 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                     }
                     __syncwarp();
                 }
-                ip = __shfl_sync(FULL_MASK, my_ipn(), nseq - 1);
+                ip = ip_next;
                 op = out1;
                 continue;
             }
@@ -346,8 +371,11 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
 
 // 48 warps per SM at 40 registers beat 32 warps at 64 despite ~140 bytes of spills (220 -> 232 GB/s): the kernel waits on
 // loads of match sources that miss L2, and more warps in flight hide more of them (measured at 8, 10, 12, 14, 16 CTAs per SM)
+#ifndef PLZ4CU_DEC_CTAS
+#define PLZ4CU_DEC_CTAS 12
+#endif
 template <bool kDict, bool kRing>
-__global__ void __launch_bounds__(kDecodeThreads, kRing ? 1 : 12)
+__global__ void __launch_bounds__(kDecodeThreads, kRing ? 1 : PLZ4CU_DEC_CTAS)
 lz4_decompress_kernel(DecodeArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn_smem[];              // kRing: 64 KiB per warp
@@ -361,6 +389,10 @@ lz4_decompress_kernel(DecodeArgs a)
 
     const uint8_t* rec = a.rec_base + a.rec_off[b];
     uint8_t* out = a.dst_base + (uint64_t)b * a.dst_stride;
+    // opaque from here on: with 40 registers the compiler would rather rebuild this pointer from blockIdx and the
+    // arguments at every use (nine instructions per load and per store of the copy loop) than keep or spill it
+    asm("" : "+l"(out));
+    __builtin_assume(__isGlobal(out));
     const uint8_t* payload;
     uint32_t csize;
     bool stored = false;
@@ -379,8 +411,7 @@ lz4_decompress_kernel(DecodeArgs a)
         }
     }
     const bool hash_on = !a.raw_blocks && a.verify_checksum != 0;    // blk/frame.go:114-127
-    const uintptr_t pa = reinterpret_cast<uintptr_t>(payload);
-    HashAlong H{hash_on && !stored, xxh32_init(lane), 0, reinterpret_cast<const uint32_t*>(pa & ~uintptr_t(3)), (uint32_t)(pa & 3u) * 8u};
+    HashAlong H{hash_on && !stored, xxh32_init(lane), 0};
 
     int32_t r;
     if (stored) {
@@ -396,7 +427,7 @@ lz4_decompress_kernel(DecodeArgs a)
         if (H.on) {
             // the rest of the payload, whatever the decoder made of it: a wrong checksum outranks a decode error
             // (the reference checks it before it decodes, blk/frame.go:114-127)
-            hash_along(H, (int)csize, lane);
+            hash_along(H, payload, (int)csize, lane);
             if (load_le32(payload + csize) != xxh32_finish_global(H.acc, payload, (uint32_t)H.done, csize, lane)) r = PLZ4CU_E_BLOCKHASH_;
         }
     }
