@@ -135,6 +135,14 @@ __device__ __noinline__ int decode_one(const uint8_t* __restrict__ src, int n, u
 // ---------------------------------------------------------------- batched decode
 
 // a byte that this kernel may have written itself (match source) or not (literal): plain global load, never the read-only path
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // (predicated in place: a branch around one load costs more than the load)
 __device__ __forceinline__ uint32_t ld_global_u8_if(const uint8_t* p, bool need)
 {
@@ -169,7 +177,7 @@ static __device__ __noinline__ void hash_along(HashAlong& H, const uint8_t* payl
 template <bool kDict, bool kRing>
 __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src, int n,
                                                 uint8_t* dst, int cap,
-                                                const uint8_t* __restrict__ dict, int dsz, int lane, uint32_t* bitmap,
+                                                const uint8_t* __restrict__ dict, int dsz, int lane, uint32_t* bitmap, uint32_t* win,
                                                 uint8_t* ring, HashAlong& H)
 {
     constexpr int kBatchBytes = 1024;               // output bytes one batch may span (32 bitmap words)
@@ -203,51 +211,62 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
             const uint32_t w0 = a0 >> 2;                        // first window word
             const uint32_t widx = w0 + (uint32_t)lane;
             const uint32_t w = (widx <= last4) ? src4[widx] : 0u;
-            // header length if a token started at each of my 4 bytes: 3 + literals, + 1 if the match nibble is 15; a
-            // literal nibble of 15 takes its extension from the byte after the token (one extension byte only)
+            // header length if a token started at each of my 4 bytes: 3 + literals, + 1 if the match nibble is 15 — the four
+            // bytes of the word at once, a nibble sum per byte (at most 19: no carry from byte to byte)
             const uint32_t wn = __shfl_down_sync(FULL_MASK, w, 1);       // lane 31 gets junk: tokens there end the batch
-            uint32_t dpack = 0;
+            const uint32_t L4 = (w >> 4) & 0x0F0F0F0Fu;
+            const uint32_t M15 = (((w & 0x0F0F0F0Fu) + 0x01010101u) >> 4) & 0x01010101u;
+            uint32_t dpack = 0x03030303u + L4 + M15;
+            // a literal nibble of 15 takes its extension from the byte after the token (one extension byte only); rare
+            const uint32_t L15 = ((L4 + 0x01010101u) >> 4) & 0x01010101u;
+            if (L15) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t tok = (w >> (8 * i)) & 0xFFu;
-                const uint32_t nxt = (i < 3 ? (w >> (8 * i + 8)) : wn) & 0xFFu;
-                uint32_t dl = 3u + (tok >> 4) + ((tok & 15u) == 15u ? 1u : 0u);
-                if ((tok >> 4) == 15u) dl = min(dl + 1u + nxt, 255u);
-                dpack |= dl << (8 * i);
-            }
-            // walk the chain through shared memory (one byte load per sequence): qb = byte offset inside the window
-            bitmap[lane] = dpack;
-            __syncwarp();
-            const uint8_t* dl8 = reinterpret_cast<const uint8_t*>(bitmap);
-            uint32_t qb = a0 & 3u;
-            uint32_t myq = 0;
-            // four steps per round, each taking effect only while the walk is inside the window (no branch per sequence)
-#pragma unroll 1
-            while (nseq < 32 && qb <= 128u - 20u) {
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const bool go = qb <= 128u - 20u;
-                    if (go && lane == nseq) myq = qb;
-                    const uint32_t step = go ? dl8[qb] : 0u;
-                    qb += step;
-                    nseq += go ? 1 : 0;
+                for (int i = 0; i < 4; i++) {
+                    if ((L15 >> (8 * i)) & 1u) {
+                        const uint32_t nxt = (i < 3 ? (w >> (8 * i + 8)) : wn) & 0xFFu;
+                        const uint32_t dl = min(((dpack >> (8 * i)) & 0xFFu) + 1u + nxt, 255u);
+                        dpack = (dpack & ~(0xFFu << (8 * i))) | (dl << (8 * i));
+                    }
                 }
             }
+            // walk the chain through shared memory.  The address register IS the walk: the area is 256-byte aligned, so
+            // the low byte of the address is the window offset, and a step is a byte store into the list of visited
+            // positions (lane k reads entry k afterwards), a byte load, and an add that saturates at the area's last
+            // byte.  Four steps per round, none of them conditional: once the walk has left the window (offset > 108)
+            // it stays out, and the entries it still writes are recognised by their value.
+            bitmap[lane] = dpack;
+            win[lane] = w;
             __syncwarp();
-            // each lane decodes its own header from the window
-            auto wbyte = [&](uint32_t bo) -> uint32_t {        // byte at window offset bo (< 128)
-                return (__shfl_sync(FULL_MASK, w, bo >> 2) >> ((bo & 3u) * 8u)) & 0xFFu;
-            };
-            const uint32_t tok = wbyte(myq);
-            const uint32_t lext = wbyte(min(myq + 1u, 127u));
+            const uint32_t area = (uint32_t)__cvta_generic_to_shared(bitmap);
+            const uint32_t qlim = area + (128u - 20u);
+            const uint32_t list0 = area + 128u;
+            uint32_t qa = area + (a0 & 3u);
+            uint32_t lp = list0;
+#pragma unroll 1
+            while (lp < list0 + 32u && qa <= qlim) {
+#pragma unroll
+                for (uint32_t u = 0; u < 4; u++) {
+                    sts_u8(lp + u, qa);
+                    qa = min(qa + lds_u8(qa), area + 255u);
+                }
+                lp += 4u;
+            }
+            __syncwarp();
+            uint32_t myq = (uint32_t)lane < lp - list0 ? lds_u8(list0 + (uint32_t)lane) : 255u;
+            nseq = __popc(__ballot_sync(FULL_MASK, myq <= 128u - 20u));     // positions ascend: the valid ones are a prefix
+            if (lane >= nseq) myq = 0;
+            // each lane decodes its own header from the window's bytes in shared memory
+            const uint32_t winb = (uint32_t)__cvta_generic_to_shared(win);
+            const uint32_t tok = lds_u8(winb + myq);
+            const uint32_t lext = lds_u8(winb + myq + 1u);
             const uint32_t L = tok >> 4, M = tok & 15u;
             const bool longlit = L == 15u;                      // literal run of 15 + one extension byte (lz4.c:2121-2128)
             const uint32_t lit = longlit ? 15u + lext : L;
-            const uint32_t lp = myq + (longlit ? 2u : 1u);      // window offset of the first literal
-            const bool inwin = lit <= (uint32_t)kMaxBatchLit && lp + lit + 2u < 128u;
-            const uint32_t ob = inwin ? lp + lit : 0u;          // window offset of the match offset
-            const uint32_t off = wbyte(ob) | (wbyte(ob + 1u) << 8);
-            const uint32_t ext = wbyte(ob + 2u);
+            const uint32_t lp1 = myq + (longlit ? 2u : 1u);     // window offset of the first literal
+            const bool inwin = lit <= (uint32_t)kMaxBatchLit && lp1 + lit + 2u < 128u;
+            const uint32_t ob = winb + (inwin ? lp1 + lit : 0u);    // where the match offset lies
+            const uint32_t off = lds_u8(ob) | (lds_u8(ob + 1u) << 8);
+            const uint32_t ext = lds_u8(ob + 2u);
             const int pos = ip + (int)(myq - (a0 & 3u));        // position of my token in src
             const int ip1 = pos + (longlit ? 2 : 1);            // first literal
             const int ipn = ip1 + (int)lit + 2 + (M == 15u ? 1 : 0);
@@ -369,17 +388,20 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
     }
 }
 
-// 48 warps per SM at 40 registers beat 32 warps at 64 despite ~140 bytes of spills (220 -> 232 GB/s): the kernel waits on
-// loads of match sources that miss L2, and more warps in flight hide more of them (measured at 8, 10, 12, 14, 16 CTAs per SM)
+// 56 warps per SM at 36 registers beat 32 warps at 64 despite the spills (measured at 8, 10, 12, 14 CTAs per SM: 14 is
+// the fastest, +5 % over 12): the kernel waits on loads of match sources that miss L2, and more warps in flight hide more of them
 #ifndef PLZ4CU_DEC_CTAS
-#define PLZ4CU_DEC_CTAS 12
+#define PLZ4CU_DEC_CTAS 14
 #endif
 template <bool kDict, bool kRing>
 __global__ void __launch_bounds__(kDecodeThreads, kRing ? 1 : PLZ4CU_DEC_CTAS)
 lz4_decompress_kernel(DecodeArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn_smem[];              // kRing: 64 KiB per warp
-    __shared__ uint32_t s_bitmap[kDecodeThreads / 32][32];
+    // per warp: 256 bytes, 256-byte aligned — header lengths of the window's 128 positions (later the bitmap of sequence
+    // starts), the list of token positions (32 bytes from byte 128), spare; and the window's 128 bytes themselves
+    __shared__ __align__(256) uint32_t s_bitmap[kDecodeThreads / 32][64];
+    __shared__ uint32_t s_win[kDecodeThreads / 32][32];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const uint32_t wpb = kRing ? 1u : (uint32_t)(kDecodeThreads / 32);
@@ -423,7 +445,7 @@ lz4_decompress_kernel(DecodeArgs a)
         r = (int32_t)csize;
     } else {
         r = decode_block<kDict, kRing>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane,
-                                       s_bitmap[warp], dyn_smem, H);
+                                       s_bitmap[warp], s_win[warp], dyn_smem, H);
         if (H.on) {
             // the rest of the payload, whatever the decoder made of it: a wrong checksum outranks a decode error
             // (the reference checks it before it decodes, blk/frame.go:114-127)
