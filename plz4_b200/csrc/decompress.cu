@@ -324,13 +324,14 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                 const uint32_t packA = (uint32_t)((orel + my_lit) & 0x7FF) | (my_off << 16);
                 const int litrel = my_litpos - orel;
                 const uint32_t lmask = (2u << lane) - 1u;
-                uint8_t* dx = dst + out0 + lane;
+                uint8_t* dx = dst + out0 + lane;                              // my byte of the chunk
+                const uint8_t* sx = src + lane;                               // ... and where it would come from as a literal, less litrel
                 int kbase = -1;                                               // sequences that start below the chunk, minus one
-                int j = 0;
-                for (int c = 0; c < total; c += 32, j++, dx += 32) {
-                    const int xr = c + lane;                                                        // byte position relative to out0
+#pragma unroll 1
+                for (int xr = lane; (xr & ~31) < total; xr += 32, dx += 32, sx += 32) {            // xr: byte position relative to out0
+                    const int ln = xr & 31;
                     // owner of the byte = last sequence starting at or before it
-                    const uint32_t sbits = __shfl_sync(FULL_MASK, my_bits, j);
+                    const uint32_t sbits = __shfl_sync(FULL_MASK, my_bits, xr >> 5);
                     const int k = kbase + __popc(sbits & lmask);
                     kbase += __popc(sbits);
                     const uint32_t ka = __shfl_sync(FULL_MASK, packA, k);
@@ -338,18 +339,18 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                     const bool live = xr < total;
                     const bool is_lit = xr < (int)(ka & 0x7FFu);
                     const int off = (int)(ka >> 16);
-                    const bool fwd = live && !is_lit && off <= lane;                                // match source inside this chunk
+                    const bool fwd = live && !is_lit && off <= ln;                                  // match source inside this chunk
                     uint32_t val = 0;
                     if (kRing) {
                         if (live && !fwd) {
                             const int s = out0 + xr - off;
-                            if (is_lit) val = src[kp + xr];
+                            if (is_lit) val = sx[kp];
                             else if (kDict && s < 0) val = dict[dsz + s];
                             else val = ring[s & 0xFFFF];
                         }
                     } else {
                         // one load from one pointer: the literal in the compressed block, or the match source `off` below me
-                        const uint8_t* p = is_lit ? src + (kp + xr) : static_cast<const uint8_t*>(dx) - off;
+                        const uint8_t* p = is_lit ? sx + kp : static_cast<const uint8_t*>(dx) - off;
                         if (kDict) {
                             const int s = out0 + xr - off;
                             if (!is_lit && s < 0) p = dict + (dsz + s);
@@ -358,7 +359,7 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                     }
                     if (__any_sync(FULL_MASK, fwd)) {
                         // forward values along in-chunk chains: root = the lane whose loaded value this byte finally equals
-                        int root = fwd ? lane - off : lane;
+                        int root = fwd ? ln - off : ln;
 #pragma unroll
                         for (int it = 0; it < 5; it++) root = __shfl_sync(FULL_MASK, root, root);
                         val = __shfl_sync(FULL_MASK, val, root);
