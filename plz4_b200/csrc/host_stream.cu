@@ -994,6 +994,7 @@ struct plz4cu_reader {
     std::vector<uint8_t> carry;
     StageClock clk;                                   // 0 source read, 1 decode, 2 wait for a batch, 3 sink write
     std::atomic<int64_t> rd_calls{0}, grow_us{0}, grows{0};
+    double ratio_seen = 0.0;                          // largest record bytes / block bytes of a batch so far (source thread only)
 
     void read_records(Batch& b, size_t want_bytes)
     {
@@ -1010,10 +1011,13 @@ struct plz4cu_reader {
         const size_t cap_max = batch_blocks * ((size_t)bsz + 8) + 64 + (bulk ? (9u << 20) : 0);
         size_t fill = 0;                                // bytes of the stream sitting in b.recs
         bool eof = false, failed = false;
+        // the record area grows with what actually arrives (a short stream never pins a full batch); once a batch has shown
+        // how the stream compresses, later areas are sized for that in one step instead of by doubling
+        const size_t expect = ratio_seen > 0.0 ? (size_t)((double)batch_blocks * (double)bsz * ratio_seen * 1.125) + (bulk ? (9u << 20) : 0) : 0;
         auto room_for = [&](size_t upto) -> bool {
             if (upto <= b.recs.cap) return true;
             const int64_t tg = StageClock::on() ? StageClock::now() : 0;
-            const bool ok = b.recs.grow(std::min(cap_max, std::max(upto, 2 * b.recs.cap)), fill);
+            const bool ok = b.recs.grow(std::min(cap_max, std::max(std::max(upto, expect), 2 * b.recs.cap)), fill);
             if (StageClock::on()) { grow_us += StageClock::now() - tg; grows++; }
             return ok;
         };
@@ -1033,7 +1037,15 @@ struct plz4cu_reader {
                     if (r != 0) { eof = true; failed = r < 0; }
                     break;
                 }
-                const size_t piece = std::max<size_t>(upto - fill, std::min<size_t>(8u << 20, std::max<size_t>(64u << 10, b.recs.cap - fill)));
+                size_t piece = std::min<size_t>(8u << 20, std::max<size_t>(64u << 10, b.recs.cap - fill));
+                if (ratio_seen > 0.0) {
+                    // near the end of the batch, read about what its remaining blocks should take: what is read beyond the
+                    // batch has to be carried over to the next one by copy
+                    const size_t ahead = fill - std::min(fill, b.recs_len);
+                    const size_t rest = (size_t)((double)(batch_blocks - nblk) * (double)bsz * ratio_seen * 1.03) + (64u << 10);
+                    piece = std::min(piece, std::max<size_t>(rest > ahead ? rest - ahead : 0, 64u << 10));
+                }
+                piece = std::max(piece, upto - fill);
                 if (!room_for(fill + piece)) { eof = true; failed = true; break; }
                 const int64_t tr0 = StageClock::on() ? StageClock::now() : 0;
                 const int64_t r = rd(ctx, b.recs.p + fill, std::min(piece, b.recs.cap - fill));
@@ -1077,6 +1089,7 @@ struct plz4cu_reader {
             nblk++;
         }
         b.nblk = nblk;
+        if (nblk > 0) ratio_seen = std::max(ratio_seen, (double)b.recs_len / ((double)nblk * (double)bsz));
         if (bulk && fill > b.recs_len) {
             const size_t extra = fill - b.recs_len;
             if (b.tail_event == 0) carry.assign(b.recs.p + b.recs_len, b.recs.p + fill);        // the body goes on
@@ -1129,8 +1142,14 @@ struct plz4cu_reader {
         next_batch_bytes = std::min(limit, next_batch_bytes * 4);
         return want;
     }
-    // batches ahead of the caller: three for small blocks (one being read, one decoding, one ready), more for large ones
-    int read_ahead_depth() const { return bsz >= (1 << 20) ? kSlots - 1 : std::min(kSlots - 1, 3); }
+    // batches ahead of the caller: four for small blocks (one being read, two decoding, one ready; 3 / 4 / 5 / 6 measured
+    // with tools/read_sweep.sh: 19-24 / 26-27 / 23-27 / 20-28 GB/s), more for large ones
+    int read_ahead_depth() const
+    {
+        static const int forced = getenv("PLZ4CU_READ_AHEAD") ? atoi(getenv("PLZ4CU_READ_AHEAD")) : 0;   // measurements
+        if (forced > 0) return std::min(kSlots - 1, forced);
+        return bsz >= (1 << 20) ? kSlots - 1 : std::min(kSlots - 1, 4);
+    }
     // source thread: read batch after batch in order, hand each to its slot's engine thread, stay at most
     // read_ahead_depth() batches ahead of the caller; ends with the batch that carries the body's tail event
     void source_loop()
