@@ -413,6 +413,7 @@ lz4_compress_kernel(EncodeArgs a)
 
     const uint8_t* src = a.src_base + a.src_off[b];
     const int n = (int)a.src_len[b];
+    if (a.split_by_size && n > 65536) return;                     // the span kernel's block
     uint8_t* rec = a.rec_base + (uint64_t)b * a.rec_stride;
     uint8_t* payload = a.raw_blocks ? rec : rec + 4;
     uint16_t* table = reinterpret_cast<uint16_t*>(smem + warp * kTableBytes);
@@ -702,6 +703,19 @@ static cudaError_t launch_frag(const FragArgs& fa, uint32_t nwarps, cudaStream_t
     return cudaGetLastError();
 }
 
+// one warp per block (round 1's encoder): blocks with a dictionary up to 64 KiB, and everything under PLZ4CU_CTA_MIN=0
+static cudaError_t launch_compress_warps(const EncodeArgs& a, cudaStream_t stream)
+{
+    dim3 grid((a.nblk + kEncodeWarps - 1) / kEncodeWarps), block(kEncodeWarps * 32);
+    const int bits = compress_hash_bits(a.dst_cap);
+    const size_t sm = (size_t)kEncodeWarps * table_bytes(bits);
+    const bool d = a.dict_size > 0;
+    if (bits == 11)      { if (d) lz4_compress_kernel<11, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<11, false><<<grid, block, sm, stream>>>(a); }
+    else if (bits == 12) { if (d) lz4_compress_kernel<12, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<12, false><<<grid, block, sm, stream>>>(a); }
+    else                 { if (d) lz4_compress_kernel<13, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<13, false><<<grid, block, sm, stream>>>(a); }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
 {
     if (a.nblk == 0) return cudaSuccess;
@@ -709,7 +723,7 @@ cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
     // No dictionary: a block of up to 64 KiB is the CTA kernel's, a larger one the span kernel's, whatever else the
     // launch holds — so a block compresses to the same bytes in any batch, stream or device (tests/test_gpu_multi.py).
     if (a.dict_size == 0 && max_len <= 65536u && g_cta_min > 0) return launch_compress_cta(a, stream);
-    if (max_len > 65536u && a.dict_size == 0 && g_spans) {
+    if (max_len > 65536u && g_spans) {
         // large blocks: spans of sixteen 64 KiB fragments, one CTA each (compress_cta.cu), then the stitch.  The cut does
         // not depend on how many blocks the launch has: a block compresses to the same bytes whatever batch, stream or
         // device it travels in (a 4 MiB block is four spans, so 64 of them — a 256 MiB file — already give every SM a CTA)
@@ -720,7 +734,7 @@ cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
         fa.e = a;
         fa.e.split_by_size = 1;
         if (a.min_src_len <= 65536u) {                       // some block may be small (or nobody knows): those first
-            cudaError_t e0 = launch_compress_cta(fa.e, stream);
+            cudaError_t e0 = a.dict_size ? launch_compress_warps(fa.e, stream) : launch_compress_cta(fa.e, stream);
             if (e0 != cudaSuccess) return e0;
         }
         fa.frags_per_block = (nfrag + span_frags - 1) / span_frags;
@@ -766,14 +780,7 @@ cudaError_t launch_compress(const EncodeArgs& a, cudaStream_t stream)
         cudaError_t e2 = cudaFreeAsync(scratch, stream);
         return e != cudaSuccess ? e : e2;
     }
-    dim3 grid((a.nblk + kEncodeWarps - 1) / kEncodeWarps), block(kEncodeWarps * 32);
-    const int bits = compress_hash_bits(a.dst_cap);
-    const size_t sm = (size_t)kEncodeWarps * table_bytes(bits);
-    const bool d = a.dict_size > 0;
-    if (bits == 11)      { if (d) lz4_compress_kernel<11, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<11, false><<<grid, block, sm, stream>>>(a); }
-    else if (bits == 12) { if (d) lz4_compress_kernel<12, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<12, false><<<grid, block, sm, stream>>>(a); }
-    else                 { if (d) lz4_compress_kernel<13, true><<<grid, block, sm, stream>>>(a); else lz4_compress_kernel<13, false><<<grid, block, sm, stream>>>(a); }
-    return cudaGetLastError();
+    return launch_compress_warps(a, stream);
 }
 
 }  // namespace plz4

@@ -793,12 +793,17 @@ lz4_compress_span_kernel(EncodeArgs a, uint8_t* tmp, uint32_t slot_stride, uint3
     const uint8_t* src = a.src_base + a.src_off[b];
     const int n_blk = (int)a.src_len[b];
     if (n_blk <= 65536) return;                                   // the CTA kernel's block
-    const int span_start = (int)(sp * span_bytes);
-    if (span_start >= n_blk && sp != 0) {
+    // With a dictionary the positions are those of a virtual block that starts with the dictionary's 64 KiB slot (the
+    // dictionary at its end, lz4.c:1556-1604: it lies just below the block): the fragment before a block's first span is
+    // then the dictionary, indexed like any fragment before a span, and offsets into it come out as plain distances.
+    const int shift = a.dict_size ? 65536 : 0;
+    const int n_v = n_blk + shift;
+    const int span_start = (int)(sp * span_bytes) + shift;
+    if (span_start >= n_v && sp != 0) {
         if (tid == 0) span_len[w] = -2;                           // this span does not exist
         return;
     }
-    const int span_end = min(n_blk, span_start + (int)span_bytes);
+    const int span_end = min(n_v, span_start + (int)span_bytes);
     uint8_t* out = tmp + (uint64_t)w * slot_stride;
 
     if (tid == 0) {
@@ -819,7 +824,8 @@ lz4_compress_span_kernel(EncodeArgs a, uint8_t* tmp, uint32_t slot_stride, uint3
     int my_x = span_start;
     int carry_x = span_start, carry_anchor = span_start, carry_out = 0;
     uint32_t it = 0;
-    for (int fs = span_start - (sp != 0 ? 65536 : 0); fs < span_end; fs += 65536, it++) {
+    const bool has_before = sp != 0 || shift != 0;                // a fragment (or the dictionary) lies before the span
+    for (int fs = span_start - (has_before ? 65536 : 0); fs < span_end; fs += 65536, it++) {
         const bool warm = fs < span_start;
         const int fe = warm ? fs + 65536 : min(fs + 65536, span_end);      // end of the fragment's bytes
         __syncthreads();                                          // every worker is done with the fragment before
@@ -829,25 +835,32 @@ lz4_compress_span_kernel(EncodeArgs a, uint8_t* tmp, uint32_t slot_stride, uint3
             for (int i = tid; i < 4096; i += kSpanThreads) d[i] = s4[i];
         }
         __syncthreads();
-        const uint8_t* fsrc = src + fs;
+        const bool dict_frag = fs < shift;                        // the dictionary's slot: zeros, then the dictionary
+        const uint8_t* fsrc = src + (fs - shift);
         const int fn = fe - fs;
-        const bool aligned = (reinterpret_cast<uintptr_t>(fsrc) & 15u) == 0;
+        const bool aligned = !dict_frag && (reinterpret_cast<uintptr_t>(fsrc) & 15u) == 0;
         const uint32_t bulk = aligned ? ((uint32_t)fn & ~15u) : 0u;
         if (tid == 0 && bulk) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the bulk copy overwrites bytes just read by ordinary loads
             mbar_arrive_expect_tx(&S.bar_load, bulk);
             tma_load_bulk(cur, fsrc, bulk, &S.bar_load);
         }
-        for (int k = (int)bulk + tid; k < fn; k += kSpanThreads) cur[k] = fsrc[k];
+        if (dict_frag) {
+            const int gap = 65536 - (int)a.dict_size;
+            for (int k = tid; k < gap; k += kSpanThreads) cur[k] = 0;
+            for (int k = tid; k < (int)a.dict_size; k += kSpanThreads) cur[gap + k] = a.dict[k];
+        } else {
+            for (int k = (int)bulk + tid; k < fn; k += kSpanThreads) cur[k] = fsrc[k];
+        }
         for (int k = fn + tid; k < fn + kWinPad && k < 65536 + kWinPad; k += kSpanThreads) cur[k] = 0;
         TileEnv env;
         env.w32 = reinterpret_cast<const uint32_t*>(S.win) + ((65536 - fs) >> 2);   // fs is a multiple of 65536
         env.win = S.win + (65536 - fs);
-        env.gsrc = src; env.payload = out; env.pos0 = fs;
-        env.lo_valid = max(0, span_start - (sp != 0 ? 65536 : 0));
-        env.hash_end = min(n_blk - 4, fe - 4);                    // five bytes at p, all of them loaded
-        env.mf_end = warm ? fs : min(n_blk - MFLIMIT + 1, fe - 3);
-        env.match_end = min(n_blk - LASTLITERALS, fe);
+        env.gsrc = src - shift; env.payload = out; env.pos0 = fs;                   // (read at block positions only)
+        env.lo_valid = sp != 0 ? span_start - 65536 : shift - (int)a.dict_size;
+        env.hash_end = min(n_v - 4, fe - 4);                      // five bytes at p, all of them loaded
+        env.mf_end = warm ? fs : min(n_v - MFLIMIT + 1, fe - 3);
+        env.match_end = min(n_v - LASTLITERALS, fe);
         env.ntiles = warm ? kMaxTiles : max(0, (env.mf_end - fs + kTile - 1) / kTile);
         env.cap = 0x7FFFFFF0; env.parity = it & 1u; env.index_only = warm;
         if (tid == 0) {

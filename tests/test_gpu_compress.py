@@ -125,6 +125,47 @@ def test_dictionary_sizes_and_block_api(gpu, codec, dn):
             assert gpu.decompress_block(c, dst_cap=len(m), dict=gd) == m
 
 
+def test_large_blocks_with_dictionary(gpu, codec):
+    """Blocks above 64 KiB with a dictionary go through the span encoder with the dictionary as the fragment before
+    the block (round 1 gave them one warp each).  The reference decodes them with the same dictionary, every block is
+    within the tolerance of liblz4 + dictionary, the dictionary is really used, and a block's bytes do not depend on
+    what else the batch holds (small blocks with a dictionary take another kernel in the same call)."""
+    from tests.datagen import logtext
+    corpus = logtext(6 << 20, seed=41)
+    for dn in (65536, 20000, 777):
+        d = corpus[100000: 100000 + dn]
+        gd, cd = gpu.Dict(d), codec.dict_create(d)
+        blocks = [d[-min(dn, 3000):] * 2 + corpus[300000: 300000 + n] for n in (66000, 200000, 1 << 20)]
+        rep = d[-min(dn, 40000):]                        # (a copy exactly 64 KiB back is out of an offset's reach)
+        blocks += [corpus[2 << 20: (2 << 20) + (3 << 20)], make("words", 300000, seed=4), rep * (200000 // len(rep) + 1)]
+        small = [corpus[50000:54096], b"", d[-200:] * 4]
+        mixed = blocks + small
+        cap = max(len(b) for b in mixed)
+        lens = [len(b) for b in mixed]
+        off = np.cumsum([0] + lens)[:-1]
+        packed, poff = gpu.compress_batch(b"".join(mixed), off, lens, gpu.compress_block_bound(cap), raw_blocks=True, dict=gd)
+        got = [packed[int(poff[i]): int(poff[i + 1])].tobytes() for i in range(len(mixed))]
+        for i, m in enumerate(mixed):
+            r, data = cd.decompress(got[i], len(m))
+            assert r == len(m) and data == m, (dn, i)
+            ref = len(cd.compress(m))
+            # (a block that is nearly one match compresses to a few hundred bytes: there a fragment boundary's 4-5 bytes and
+            # a first match that starts some dozen bytes later are percents of nothing — a thousandth of the input is allowed)
+            assert len(got[i]) <= max(ref * TOLERANCE, ref + len(m) // 1000 + 16), (dn, i, len(got[i]), ref)
+        # the dictionary is used: the block that repeats it costs next to nothing, and far less than without it
+        assert len(got[len(blocks) - 1]) < 0.02 * len(blocks[-1]) + 64
+        if dn >= 20000:
+            assert len(got[0]) < len(codec.compress(blocks[0]))
+        # alone, a large block gives the same bytes as in the batch (small blocks with a dictionary keep round 1's encoder,
+        # whose table size follows the capacity the call states)
+        for i in (0, 2):
+            assert gpu.compress_block(mixed[i], dict=gd) == got[i], (dn, i)
+        # and back through the GPU decoder
+        out, res = gpu.decompress_batch(packed, poff[:-1], cap, raw_len=np.diff(poff).astype(np.uint32), dict=gd)
+        for i, m in enumerate(mixed):
+            assert res[i] == len(m) and out[i, : len(m)].tobytes() == m, (dn, i)
+
+
 def test_compress_is_deterministic(gpu):
     """The same bytes compress to the same bytes whatever the timing between a block's tiles (stream writers rely on it:
     progress marks of one run address the frame of another, tests/test_gpu_frame_device.py)."""

@@ -50,4 +50,24 @@ for kind in KINDS_:
             out = np.zeros(max(n, 1), dtype=np.uint8); cudamemcpy(out.ctypes.data, d_out, max(n, 1), 2) if n else None
             assert ol[0] == n and out[:n].tobytes() == data.tobytes(), (kind, n, misalign, ol[0])
             for p in (d_src, d_rec, d_off, d_len, d_rl, d_in, d_out, d_ol): L.plz4cu_device_free(p)
+# large blocks with a dictionary: the span encoder with the dictionary as the fragment before the block
+for dn in ([65536, 777] if FAST != "2" else [777]):
+    dct = make("log", dn, seed=3)
+    L.plz4cu_dict_create.restype = C.c_void_p; L.plz4cu_dict_create.argtypes = [C.c_char_p, C.c_size_t]
+    gd = L.plz4cu_dict_create(dct, len(dct)); assert gd
+    for n in (70000, 300001):
+        data = np.frombuffer(dct[-500:] + make("log", n - 500, seed=4), dtype=np.uint8)
+        d_src = dev((n + 15) // 16 * 16); cudamemcpy(d_src, data.ctypes.data, n, 1)
+        cap = int(L.plz4cu_compress_bound(n)); stride = (cap + 8 + 15) // 16 * 16
+        d_rec = dev(stride); d_off = dev(8); d_len = dev(4); d_rl = dev(4)
+        off = np.array([0], dtype=np.uint64); ln = np.array([n], dtype=np.uint32)
+        cudamemcpy(d_off, off.ctypes.data, 8, 1); cudamemcpy(d_len, ln.ctypes.data, 4, 1)
+        check(L.plz4cu_compress_batch_device(None, d_src, d_off, d_len, 1, cap, 1, 0, C.c_void_p(gd), d_rec, stride, d_rl))
+        rl = np.zeros(1, dtype=np.uint32); cudamemcpy(rl.ctypes.data, d_rl, 4, 2)
+        d_out = dev(cap + 16); d_ol = dev(4)
+        check(L.plz4cu_decompress_batch_device(None, d_rec, d_off, None, 1, cap, 1, 0, C.c_void_p(gd), d_out, cap + 16, d_ol))
+        ol = np.zeros(1, dtype=np.int32); cudamemcpy(ol.ctypes.data, d_ol, 4, 2)
+        out = np.zeros(n, dtype=np.uint8); cudamemcpy(out.ctypes.data, d_out, n, 2)
+        assert ol[0] == n and out.tobytes() == data.tobytes(), (dn, n, ol[0])
+        for p in (d_src, d_rec, d_off, d_len, d_rl, d_out, d_ol): L.plz4cu_device_free(p)
 print("sanitize workload ok")
