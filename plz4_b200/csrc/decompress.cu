@@ -405,6 +405,8 @@ lz4_decompress_kernel(DecodeArgs a)
     __shared__ uint32_t s_win[kDecodeThreads / 32][32];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
+    // the token walk stores the low byte of a shared-memory address as a window offset: the area must sit on a 256-byte line
+    if (((uint32_t)__cvta_generic_to_shared(&s_bitmap[0][0]) & 255u) != 0u) __trap();
     const uint32_t wpb = kRing ? 1u : (uint32_t)(kDecodeThreads / 32);
     if (kRing && warp != 0) return;
     const uint32_t b = blockIdx.x * wpb + warp;
