@@ -674,12 +674,16 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
     const uint32_t slot_payload = std::max(dst_cap, max_len);
     const uint32_t stride = round_up16(slot_payload + (raw_blocks ? 0 : PLZ4CU_REC_OVERHEAD));
 
+    // blocks a chunk should hold at least: 256 of up to 64 KiB; large blocks are spans of 1 MiB to the encoder, so 32 MiB of
+    // them fill the lanes as well, and a stream's batch of 4 MiB blocks (32 of them) pipelines instead of going up, through
+    // the kernels and down in one piece
+    const uint32_t chunk_blocks = std::max<uint32_t>(1, std::min<uint64_t>(kChunkBlocks, (32ull << 20) / std::max<uint32_t>(max_len, 1)));
     std::vector<Chunk> chunks;
     for (uint32_t b = 0; b < nblk;) {
         Chunk c{b, b, src_off[b], src_off[b] + src_len[b]};
         while (c.b1 < nblk) {
             uint64_t lo = std::min(c.lo, src_off[c.b1]), hi = std::max(c.hi, src_off[c.b1] + src_len[c.b1]);
-            if (c.b1 > c.b0 && (hi - lo > kChunkBytes || (c.b1 - c.b0 >= kChunkBlocks && c.hi - c.lo >= chunk_min))) break;
+            if (c.b1 > c.b0 && (hi - lo > kChunkBytes || (c.b1 - c.b0 >= chunk_blocks && c.hi - c.lo >= chunk_min))) break;
             c.lo = lo; c.hi = hi; c.b1++;
         }
         chunks.push_back(c);

@@ -29,7 +29,7 @@ for i in range(n // seg):
 other = np.empty(n, dtype=np.uint8)
 fbuf = np.empty(n + (16 << 20), dtype=np.uint8)
 gb = lambda t: "%.2f GB/s (%.0f ms)" % (n / t / 1e9, t * 1e3)
-for nd in sorted({1, 2, ndev} & set(range(1, ndev + 1))):
+for nd in sorted({1, 2, 4, ndev} & set(range(1, ndev + 1))):
     o = dict(block_size_idx=5, block_checksum=True, content_checksum=False, n_devices=nd)
     flen = c_compress(data, fbuf, **o)
     tw = best(lambda: c_compress(data, fbuf, **o), 2)
