@@ -1136,8 +1136,10 @@ struct plz4cu_reader {
     {
         const size_t limit = opt.batch_bytes(bsz, true);
         if (!async) return limit;
-        // first batch: 64 blocks (a batch costs at least one block's decode time, so large blocks start large)
-        if (next_batch_bytes == 0) next_batch_bytes = std::max<size_t>(64 * (size_t)bsz, 1u << 20);
+        // first batch: 4 MiB of small blocks, four large ones — the caller (and the serial content checksum behind it) gets its
+        // first bytes after one block's decode time; the batches that follow are four times as large each and decode
+        // beside one another, so the stream's rate does not depend on the small start
+        if (next_batch_bytes == 0) next_batch_bytes = bsz >= (1 << 20) ? 4 * (size_t)bsz : std::max<size_t>(64 * (size_t)bsz, 1u << 20);
         const size_t want = std::min(next_batch_bytes, limit);
         next_batch_bytes = std::min(limit, next_batch_bytes * 4);
         return want;
