@@ -68,12 +68,12 @@ fbuf = np.empty(data.size + (1 << 20), dtype=np.uint8); obuf = np.empty(data.siz
 o0 = dict(block_size_idx=7, block_checksum=True, content_checksum=True, parallel=-1)
 flen = c_compress(data, fbuf, **o0)
 assert c_decompress(fbuf, flen, obuf, parallel=-1) == data.size and obuf.tobytes() == raw
-tw = best(lambda: c_compress(data, fbuf, **o0), 2)
-tr = best(lambda: c_decompress(fbuf, flen, obuf, parallel=-1), 2)
+tw = best(lambda: c_compress(data, fbuf, **o0), 4)
+tr = best(lambda: c_decompress(fbuf, flen, obuf, parallel=-1), 4)
 o0n = dict(o0, content_checksum=False)
 flen_n = c_compress(data, fbuf, **o0n)
-tw_n = best(lambda: c_compress(data, fbuf, **o0n), 2)
-tr_n = best(lambda: c_decompress(fbuf, flen_n, obuf, parallel=-1), 2)
+tw_n = best(lambda: c_compress(data, fbuf, **o0n), 4)
+tr_n = best(lambda: c_decompress(fbuf, flen_n, obuf, parallel=-1), 4)
 frame = bytes(flen)
 cc, cd, cr = cpu_blocks(data, 4 << 20)
 res["config0_256MiB_4MiB_blocks_bx_cx_streams"] = {
