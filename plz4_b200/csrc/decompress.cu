@@ -231,23 +231,23 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
             }
             // walk the chain through shared memory.  The address register IS the walk: the area is 256-byte aligned, so
             // the low byte of the address is the window offset, and a step is a byte store into the list of visited
-            // positions (lane k reads entry k afterwards), a byte load, and an add that saturates at the area's last
-            // byte.  Four steps per round, none of them conditional: once the walk has left the window (offset > 108)
+            // positions (lane k reads entry k afterwards), a byte load, and an add that saturates below the list (byte
+            // 191: nothing is ever written between the header lengths and there).  Four steps per round, none of them conditional: once the walk has left the window (offset > 108)
             // it stays out, and the entries it still writes are recognised by their value.
             bitmap[lane] = dpack;
             win[lane] = w;
             __syncwarp();
             const uint32_t area = (uint32_t)__cvta_generic_to_shared(bitmap);
             const uint32_t qlim = area + (128u - 20u);
-            const uint32_t list0 = area + 128u;
+            const uint32_t list0 = area + 192u;                 // (above the clamp: the walk never reads what it lists)
             uint32_t qa = area + (a0 & 3u);
             uint32_t lp = list0;
 #pragma unroll 1
             while (lp < list0 + 32u && qa <= qlim) {
 #pragma unroll
                 for (uint32_t u = 0; u < 4; u++) {
-                    sts_u8(lp + u, qa);
-                    qa = min(qa + lds_u8(qa), area + 255u);
+                    if (lane == 0) sts_u8(lp + u, qa);          // (every lane walks the same chain; one of them keeps the list)
+                    qa = min(qa + lds_u8(qa), area + 191u);
                 }
                 lp += 4u;
             }
@@ -400,7 +400,8 @@ lz4_decompress_kernel(DecodeArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn_smem[];              // kRing: 64 KiB per warp
     // per warp: 256 bytes, 256-byte aligned — header lengths of the window's 128 positions (later the bitmap of sequence
-    // starts), the list of token positions (32 bytes from byte 128), spare; and the window's 128 bytes themselves
+    // starts), spare (the walk's steps past the window read here), the list of token positions (32 bytes from byte 192);
+    // and the window's 128 bytes themselves
     __shared__ __align__(256) uint32_t s_bitmap[kDecodeThreads / 32][64];
     __shared__ uint32_t s_win[kDecodeThreads / 32][32];
     const int lane = lane_id();
