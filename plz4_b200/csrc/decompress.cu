@@ -174,12 +174,52 @@ static __device__ __noinline__ void hash_along(HashAlong& H, const uint8_t* payl
     }
 }
 
-template <bool kDict, bool kRing>
+// ---- two warps per block ("duo"): one parses (walk, headers, scan, checks) and publishes batches, the other produces the
+// bytes.  Both contexts hide latency, but they share ONE block: half as many 64 KiB output windows are in flight per SM as with
+// a block per warp at the same occupancy, and neither warp carries the other's registers.
+struct DuoSlot {
+    uint32_t packA[32];         // per sequence: where its match starts (relative to out0) | offset << 16
+    int litrel[32];             // per sequence: literal for the byte at batch position x is src[litrel + x]
+    uint32_t bits[32];          // bitmap of sequence starts over the batch's output range
+};
+#ifndef PLZ4CU_DUO_RING
+#define PLZ4CU_DUO_RING 2
+#endif
+constexpr int kDuoRing = PLZ4CU_DUO_RING;         // batches between parser and copier (a power of two)
+struct DuoShared {
+    DuoSlot slot[kDuoRing];
+    int out0[kDuoRing], total[kDuoRing];
+    volatile int published;     // batches the parser has listed
+    volatile int taken;         // batches the copier has read into registers (their slots are free)
+    volatile int copied;        // batches whose bytes are all written
+    volatile int quit;          // the parser lists nothing more
+};
+constexpr int kDuoSpinLimit = 1 << 24;
+#ifndef PLZ4CU_DUO_NAP
+#define PLZ4CU_DUO_NAP 2000
+#endif
+
+// wait until *counter >= want (a nap between polls: a waiting warp takes no issue slots from the working ones)
+__device__ __forceinline__ void duo_wait(const volatile int* counter, int want, int lane)
+{
+    for (int spins = 0;; spins++) {
+        int v = 0;
+        if (lane == 0) v = *counter;
+        v = __shfl_sync(FULL_MASK, v, 0);
+        if (v >= want) break;
+        if (spins > kDuoSpinLimit) __trap();
+        __nanosleep(PLZ4CU_DUO_NAP);
+    }
+    __threadfence_block();
+}
+
+template <bool kDict, bool kRing, bool kDuo = false>
 __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src, int n,
                                                 uint8_t* dst, int cap,
                                                 const uint8_t* __restrict__ dict, int dsz, int lane, uint32_t* bitmap, uint32_t* win,
-                                                uint8_t* ring, HashAlong& H)
+                                                uint8_t* ring, HashAlong& H, DuoShared* D = nullptr)
 {
+    int nb = 0;                                     // kDuo: batches published
     constexpr int kBatchBytes = 1024;               // output bytes one batch may span (32 bitmap words)
     constexpr int kMaxBatchLit = 63;                // longest literal run a batched sequence may carry (6 bits)
     if (cap == 0) return (n == 1 && src[0] == 0) ? 0 : -1;
@@ -323,6 +363,19 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
                 // (literal for the byte at batch position x: src[litrel + x])
                 const uint32_t packA = (uint32_t)((orel + my_lit) & 0x7FF) | (my_off << 16);
                 const int litrel = my_litpos - orel;
+                if (kDuo) {
+                    // hand the batch to the copier: its slot is free once the batch that was there has been taken
+                    duo_wait(&D->taken, nb - (kDuoRing - 1), lane);
+                    DuoSlot& sl = D->slot[nb & (kDuoRing - 1)];
+                    sl.packA[lane] = packA; sl.litrel[lane] = litrel; sl.bits[lane] = my_bits;
+                    if (lane == 0) { D->out0[nb & (kDuoRing - 1)] = out0; D->total[nb & (kDuoRing - 1)] = total; }
+                    __syncwarp();
+                    if (lane == 0) { __threadfence_block(); D->published = nb + 1; }
+                    nb++;
+                    ip = ip_next;
+                    op = out1;
+                    continue;
+                }
                 const uint32_t lmask = (2u << lane) - 1u;
                 uint8_t* dx = dst + out0 + lane;                              // my byte of the chunk
                 const uint8_t* sx = src + lane;                               // ... and where it would come from as a literal, less litrel
@@ -379,6 +432,7 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
         // ---- anything that is not a shortcut sequence: one sequence through the literal state machine
         int32_t ret = 0;
         const int op_before = op;
+        if (kDuo) duo_wait(&D->copied, nb, lane);       // decode_one reads and writes the output itself: everything listed is there
         if (decode_one<kDict>(src, n, dst, cap, dict, dsz, lane, ip, op, ret) == kStepDone) return ret;
         __syncwarp();                                   // its stores may be the next batch's match sources
         if (kRing) {
@@ -453,6 +507,134 @@ lz4_decompress_kernel(DecodeArgs a)
         if (H.on) {
             // the rest of the payload, whatever the decoder made of it: a wrong checksum outranks a decode error
             // (the reference checks it before it decodes, blk/frame.go:114-127)
+            hash_along(H, payload, (int)csize, lane);
+            if (load_le32(payload + csize) != xxh32_finish_global(H.acc, payload, (uint32_t)H.done, csize, lane)) r = PLZ4CU_E_BLOCKHASH_;
+        }
+    }
+    if (lane == 0) a.out_len[b] = r;
+}
+
+// the copier of a duo: takes the batches in order and produces their bytes (decode_block step 3)
+template <bool kDict>
+__device__ __forceinline__ void duo_copy(DuoShared* D, const uint8_t* __restrict__ src, uint8_t* dst,
+                                         const uint8_t* __restrict__ dict, int dsz, int lane)
+{
+    const uint32_t lmask = (2u << lane) - 1u;
+    for (int k = 0;; k++) {
+        for (int spins = 0;; spins++) {
+            int v = 0;
+            if (lane == 0) { const int q = D->quit; const int p = D->published; v = p > k ? 1 : (q ? -1 : 0); }   // quit first: it is raised last
+            v = __shfl_sync(FULL_MASK, v, 0);
+            if (v > 0) break;
+            if (v < 0) return;
+            if (spins > kDuoSpinLimit) __trap();
+            __nanosleep(PLZ4CU_DUO_NAP);
+        }
+        __threadfence_block();
+        const DuoSlot& sl = D->slot[k & (kDuoRing - 1)];
+        const uint32_t packA = sl.packA[lane];
+        const int litrel = sl.litrel[lane];
+        const uint32_t my_bits = sl.bits[lane];
+        const int out0 = D->out0[k & (kDuoRing - 1)], total = D->total[k & (kDuoRing - 1)];
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); D->taken = k + 1; }
+        uint8_t* dx = dst + out0 + lane;                              // my byte of the chunk
+        const uint8_t* sx = src + lane;                               // ... and where it would come from as a literal, less litrel
+        int kbase = -1;                                               // sequences that start below the chunk, minus one
+#pragma unroll 1
+        for (int xr = lane; (xr & ~31) < total; xr += 32, dx += 32, sx += 32) {
+            const int ln = xr & 31;
+            const uint32_t sbits = __shfl_sync(FULL_MASK, my_bits, xr >> 5);
+            const int q = kbase + __popc(sbits & lmask);
+            kbase += __popc(sbits);
+            const uint32_t ka = __shfl_sync(FULL_MASK, packA, q);
+            const int kp = __shfl_sync(FULL_MASK, litrel, q);
+            const bool live = xr < total;
+            const bool is_lit = xr < (int)(ka & 0x7FFu);
+            const int off = (int)(ka >> 16);
+            const bool fwd = live && !is_lit && off <= ln;
+            const uint8_t* p = is_lit ? sx + kp : static_cast<const uint8_t*>(dx) - off;
+            if (kDict) {
+                const int s = out0 + xr - off;
+                if (!is_lit && s < 0) p = dict + (dsz + s);
+            }
+            uint32_t val = ld_global_u8_if(p, live && !fwd);
+            if (__any_sync(FULL_MASK, fwd)) {
+                int root = fwd ? ln - off : ln;
+#pragma unroll
+                for (int it = 0; it < 5; it++) root = __shfl_sync(FULL_MASK, root, root);
+                val = __shfl_sync(FULL_MASK, val, root);
+            }
+            if (live) *dx = (uint8_t)val;
+            __syncwarp();
+        }
+        if (lane == 0) { __threadfence_block(); D->copied = k + 1; }
+    }
+}
+
+// two blocks per CTA, two warps per block
+#ifndef PLZ4CU_DUO_CTAS
+#define PLZ4CU_DUO_CTAS 16
+#endif
+template <bool kDict>
+__global__ void __launch_bounds__(kDecodeThreads, PLZ4CU_DUO_CTAS)
+lz4_decompress_duo_kernel(DecodeArgs a)
+{
+    constexpr int kPairs = kDecodeThreads / 64;
+    __shared__ __align__(256) uint32_t s_bitmap[kPairs][64];
+    __shared__ uint32_t s_win[kPairs][32];
+    __shared__ DuoShared s_duo[kPairs];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int pair = warp >> 1;
+    const bool copier = (warp & 1) != 0;
+    if (((uint32_t)__cvta_generic_to_shared(&s_bitmap[0][0]) & 255u) != 0u) __trap();
+    if (threadIdx.x < kPairs) { s_duo[threadIdx.x].published = 0; s_duo[threadIdx.x].taken = 0; s_duo[threadIdx.x].copied = 0; s_duo[threadIdx.x].quit = 0; }
+    __syncthreads();
+    const uint32_t b = blockIdx.x * kPairs + pair;
+    if (b >= a.nblk) return;
+    DuoShared* D = &s_duo[pair];
+
+    const uint8_t* rec = a.rec_base + a.rec_off[b];
+    uint8_t* out = a.dst_base + (uint64_t)b * a.dst_stride;
+    asm("" : "+l"(out));
+    __builtin_assume(__isGlobal(out));
+    const uint8_t* payload;
+    uint32_t csize;
+    bool stored = false;
+    if (a.raw_blocks) {
+        payload = rec;
+        csize = a.raw_len[b];
+    } else {
+        uint32_t word = load_le32(rec);
+        stored = (word & 0x80000000u) != 0;
+        csize = word & 0x7FFFFFFFu;
+        payload = rec + 4;
+        if (csize > a.dst_cap) {                                  // blk/frame.go:79-81
+            if (lane == 0 && !copier) a.out_len[b] = PLZ4CU_E_OVERFLOW_;
+            return;
+        }
+    }
+    if (copier) {
+        if (!stored) duo_copy<kDict>(D, payload, out, a.dict, (int)a.dict_size, lane);
+        return;
+    }
+    const bool hash_on = !a.raw_blocks && a.verify_checksum != 0;    // blk/frame.go:114-127
+    HashAlong H{hash_on && !stored, xxh32_init(lane), 0};
+    int32_t r;
+    if (stored) {
+        if (hash_on && load_le32(payload + csize) != warp_xxh32(payload, csize, lane)) {
+            if (lane == 0) a.out_len[b] = PLZ4CU_E_BLOCKHASH_;
+            return;
+        }
+        warp_copy(out, payload, csize, lane);
+        r = (int32_t)csize;
+    } else {
+        r = decode_block<kDict, false, true>(payload, (int)csize, out, (int)a.dst_cap, a.dict, (int)a.dict_size, lane,
+                                             s_bitmap[pair], s_win[pair], nullptr, H, D);
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); D->quit = 1; }       // (every path out of decode_block: the copier must end)
+        if (H.on) {
             hash_along(H, payload, (int)csize, lane);
             if (load_le32(payload + csize) != xxh32_finish_global(H.acc, payload, (uint32_t)H.done, csize, lane)) r = PLZ4CU_E_BLOCKHASH_;
         }
@@ -1114,6 +1296,7 @@ int g_team_pair = -1;                           // two teams per SM: -1 when the
 int g_team_ring = 65536;                        // output window of a lone team, bytes (PLZ4CU_TEAM_RING: 65536 or 131072)
 int g_team_copy = 16;                           // copy warps of a lone team (PLZ4CU_TEAM_COPY); paired teams have 8
 int g_team_dbg = 0;                             // PLZ4CU_TEAM_DBG: measurement switches of the team kernel (wrong output)
+int g_dec_duo = 0;                              // PLZ4CU_DEC_DUO=1: two warps per block (parser + copier) for launches of many blocks
 int g_team = 1;                                 // PLZ4CU_TEAM=0: few large blocks go back to one warp per block (measurements);
                                                 // =2: every launch below kRingBlocks blocks takes the team kernel (tests)
 
@@ -1133,6 +1316,7 @@ cudaError_t configure_decompress()
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     }
+    if (const char* v = getenv("PLZ4CU_DEC_DUO")) g_dec_duo = atoi(v);
     if (const char* v = getenv("PLZ4CU_TEAM_PAIR")) g_team_pair = atoi(v);
     if (const char* v = getenv("PLZ4CU_TEAM_RING")) { const int r = atoi(v); if (r == 65536 || r == 131072) g_team_ring = r; }
     if (const char* v = getenv("PLZ4CU_TEAM")) g_team = atoi(v);
@@ -1167,6 +1351,13 @@ cudaError_t launch_decompress(const DecodeArgs& a, cudaStream_t stream)
         dim3 grid(a.nblk), block(32);
         if (a.dict_size > 0) lz4_decompress_kernel<true, true><<<grid, block, kRingBytes, stream>>>(a);
         else lz4_decompress_kernel<false, true><<<grid, block, kRingBytes, stream>>>(a);
+        return cudaGetLastError();
+    }
+    if (g_dec_duo) {
+        const uint32_t ppb = kDecodeThreads / 64;
+        dim3 grid((a.nblk + ppb - 1) / ppb), block(kDecodeThreads);
+        if (a.dict_size > 0) lz4_decompress_duo_kernel<true><<<grid, block, 0, stream>>>(a);
+        else lz4_decompress_duo_kernel<false><<<grid, block, 0, stream>>>(a);
         return cudaGetLastError();
     }
     const uint32_t wpb = kDecodeThreads / 32;
