@@ -1296,7 +1296,8 @@ int g_team_pair = -1;                           // two teams per SM: -1 when the
 int g_team_ring = 65536;                        // output window of a lone team, bytes (PLZ4CU_TEAM_RING: 65536 or 131072)
 int g_team_copy = 16;                           // copy warps of a lone team (PLZ4CU_TEAM_COPY); paired teams have 8
 int g_team_dbg = 0;                             // PLZ4CU_TEAM_DBG: measurement switches of the team kernel (wrong output)
-int g_dec_duo = 0;                              // PLZ4CU_DEC_DUO=1: two warps per block (parser + copier) for launches of many blocks
+int g_dec_duo = -1;                             // PLZ4CU_DEC_DUO: 1 = two warps per block (parser + copier) always, 0 = never,
+                                                // -1 = when one warp per block would leave half of the SMs' warp slots empty
 int g_team = 1;                                 // PLZ4CU_TEAM=0: few large blocks go back to one warp per block (measurements);
                                                 // =2: every launch below kRingBlocks blocks takes the team kernel (tests)
 
@@ -1353,7 +1354,10 @@ cudaError_t launch_decompress(const DecodeArgs& a, cudaStream_t stream)
         else lz4_decompress_kernel<false, true><<<grid, block, kRingBytes, stream>>>(a);
         return cudaGetLastError();
     }
-    if (g_dec_duo) {
+    // A launch that cannot fill the SMs with one warp per block (fewer than 32 blocks per SM) gives every block two: twice the
+    // contexts to hide latency with (4096 blocks of 256 KiB: 197 -> 245 GB/s, 1024 blocks of 1 MiB: 75 -> 105); a launch
+    // that can takes the one-warp kernel, which executes 13 % fewer instructions.
+    if (g_dec_duo > 0 || (g_dec_duo < 0 && a.nblk <= (uint32_t)g_sm_count * 32u)) {
         const uint32_t ppb = kDecodeThreads / 64;
         dim3 grid((a.nblk + ppb - 1) / ppb), block(kDecodeThreads);
         if (a.dict_size > 0) lz4_decompress_duo_kernel<true><<<grid, block, 0, stream>>>(a);

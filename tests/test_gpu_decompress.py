@@ -177,12 +177,14 @@ def test_dictionary_decode(gpu, port, codec):
     assert res2[0] < 0 or out2[0, : res2[0]].tobytes() != srcs[-1]
 
 
-def test_whole_decode_suite_through_the_two_warp_decoder():
-    """PLZ4CU_DEC_DUO=1 gives a block two warps (one parses and lists batches, one produces the bytes: half the output windows
-    in flight, 1.3-1.7x the algorithmic DRAM traffic instead of 3.3x, 9 % slower): bytes and return codes must be those of
-    the one-warp decoder, so its whole parity suite and the at-scale configs run again through it."""
+@pytest.mark.parametrize("duo", ["0", "1"])
+def test_whole_decode_suite_through_either_decoder(duo):
+    """Launches that cannot fill the SMs with one warp per block give a block two warps (one parses and lists batches, one
+    produces the bytes: lz4_decompress_duo_kernel), the others one (lz4_decompress_kernel); PLZ4CU_DEC_DUO=0 / 1 forces
+    either for every launch.  Bytes and return codes must be the same: the whole parity suite, the at-scale configs and the
+    streams run through each."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PLZ4CU_DEC_DUO="1")
+    env = dict(os.environ, PLZ4CU_DEC_DUO=duo)
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k", "not whole_decode_suite",
                         "tests/test_gpu_decompress.py", "tests/test_gpu_configs.py", "tests/test_gpu_stream.py"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=1500)
