@@ -11,6 +11,8 @@
  * exactly (a record slot up to its record length, an output slot up to the decoded length).  The HOST decompress entry
  * points copy whole dst_cap-wide slots back: bytes of a slot beyond out_len[b], and the whole slot of a failed block,
  * are unspecified (they come from a scratch buffer the engine reuses) — read out_len[b] bytes, no more.
+ * Host buffers may be page-locked (plz4cu_host_alloc, cudaHostAlloc, cudaHostRegister: copied by DMA in place, ~49 GB/s) or
+ * ordinary pageable memory (staged through the engine's own pinned slabs by several host threads, ~26-32 GB/s).
  *
  * Block record layout (identical to blk.CompressToBlk, internal/pkg/blk/blk.go:87-106):
  *     [ LE32 size | bit31 = stored uncompressed ][ payload ][ LE32 xxh32(payload) if block checksum ]

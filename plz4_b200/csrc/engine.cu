@@ -25,6 +25,8 @@ static_assert(PLZ4CU_E_BLOCKHASH == PLZ4CU_E_BLOCKHASH_, "header/kernels mismatc
 static_assert(PLZ4CU_E_OVERFLOW == PLZ4CU_E_OVERFLOW_, "header/kernels mismatch");
 static_assert(PLZ4CU_E_STALL == PLZ4CU_E_STALL_, "header/kernels mismatch");
 
+void plz4cu_internal_copy(void* dst, const void* src, size_t n);    // host_stream.cu: copy by several threads
+
 namespace {
 
 std::mutex g_slab_mu;
@@ -54,6 +56,7 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess)
 // host pipeline tunables (see "host-resident batches" below)
 constexpr int kMaxLanes = 8;
 int kLanes = 4;                                  // lanes in use                   (PLZ4CU_LANES)
+bool g_stage_pageable = true;                    // pageable caller buffers go through pinned slabs, several threads (PLZ4CU_STAGE=0: straight cudaMemcpyAsync)
 bool g_spin_wait = false;                        // busy-wait on the GPU instead of sleeping (PLZ4CU_SPIN, measurements)
 uint32_t kChunkBlocks = 256;                     // blocks per chunk we aim for    (PLZ4CU_CHUNK_BLOCKS)
 uint64_t kChunkMinBytes = 16ull << 20;           // ... but small payloads are gathered up to this many bytes (PLZ4CU_CHUNK_MIB)
@@ -66,6 +69,7 @@ void read_tuning_env()
         if (const char* e = getenv("PLZ4CU_LANES")) { int v = atoi(e); if (v >= 1 && v <= kMaxLanes) kLanes = v; }
         if (const char* e = getenv("PLZ4CU_CHUNK_BLOCKS")) { int v = atoi(e); if (v >= 1) kChunkBlocks = (uint32_t)v; }
         if (const char* e = getenv("PLZ4CU_SPIN")) g_spin_wait = atoi(e) != 0;
+        if (const char* e = getenv("PLZ4CU_STAGE")) g_stage_pageable = atoi(e) != 0;
         if (const char* e = getenv("PLZ4CU_CHUNK_MIB")) { int v = atoi(e); if (v >= 1) kChunkMinBytes = (uint64_t)v << 20; }
     });
 }
@@ -123,6 +127,15 @@ struct HostBuf {
 };
 
 // one pipeline lane: a stream plus its private scratch
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Pageable buffers are staged through the lanes' pinned
+// slabs by several host threads: a pageable cudaMemcpyAsync goes through the driver's own bounce buffer at 9-11 GB/s.
+static bool host_pinned(const void* p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged || at.type == cudaMemoryTypeDevice;
+}
+
 struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;          // sizes of a compressed chunk are on the host
@@ -130,6 +143,8 @@ struct Lane {
     bool fin_recorded = false;
     DevBuf in, out, packed, off, res, poff;
     HostBuf h_meta, h_res;      // pinned staging for small metadata (up / down)
+    HostBuf h_in, h_out;        // pinned staging for a caller's pageable buffers (one chunk up, one chunk down)
+    uint64_t out_pos = 0, out_bytes = 0;   // where the chunk's bytes go in the caller's buffer once they are down
 };
 
 struct Pipe {
@@ -691,6 +706,7 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
     }
     const int nchunks = (int)chunks.size();
     uint64_t out_pos = 0;
+    const bool stage_in = g_stage_pageable && !host_pinned(hsrc), stage_out = g_stage_pageable && !host_pinned(hout);
 
     // stage 1: inputs up, kernels, packed offsets down
     auto issue = [&](int k) -> int {
@@ -709,7 +725,13 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         uint64_t* h_rel = L.h_meta.as<uint64_t>();
         uint32_t* h_len = reinterpret_cast<uint32_t*>(h_rel + cnt);
         for (uint32_t i = 0; i < cnt; i++) { h_rel[i] = src_off[c.b0 + i] - c.lo; h_len[i] = src_len[c.b0 + i]; }
-        CU(cudaMemcpyAsync(L.in.p, hsrc + c.lo, span, cudaMemcpyHostToDevice, L.st));
+        const uint8_t* up = hsrc + c.lo;
+        if (stage_in) {
+            CU(L.h_in.reserve(span));
+            plz4cu_internal_copy(L.h_in.p, up, span);
+            up = L.h_in.as<uint8_t>();
+        }
+        CU(cudaMemcpyAsync(L.in.p, up, span, cudaMemcpyHostToDevice, L.st));
         CU(cudaMemcpyAsync(L.off.p, h_rel, (uint64_t)cnt * 12, cudaMemcpyHostToDevice, L.st));
         EncodeArgs a{};
         a.src_base = L.in.as<uint8_t>(); a.src_off = L.off.as<uint64_t>();
@@ -735,7 +757,10 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         const uint64_t* hoff = L.h_res.as<uint64_t>();
         const uint64_t total = hoff[cnt];
         if (out_pos + total > packed_cap) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: packed buffer too small");
-        CU(cudaMemcpyAsync(hout + out_pos, L.packed.p, total, cudaMemcpyDeviceToHost, L.st));
+        uint8_t* down = hout + out_pos;
+        L.out_pos = out_pos; L.out_bytes = stage_out ? total : 0;
+        if (stage_out) { CU(L.h_out.reserve(total)); down = L.h_out.as<uint8_t>(); }
+        CU(cudaMemcpyAsync(down, L.packed.p, total, cudaMemcpyDeviceToHost, L.st));
         CU(cudaEventRecord(L.fin, L.st));
         L.fin_recorded = true;
         for (uint32_t i = 0; i <= cnt; i++) packed_off[c.b0 + i] = out_pos + hoff[i];
@@ -746,6 +771,7 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         Lane& L = pp->lane[k % kLanes];
         if (L.fin_recorded) CU(cudaEventSynchronize(L.fin));
         else CU(cudaStreamSynchronize(L.st));             // error path: the chunk never got as far as post()
+        if (L.fin_recorded && L.out_bytes) { plz4cu_internal_copy(hout + L.out_pos, L.h_out.p, L.out_bytes); L.out_bytes = 0; }
         return 0;
     };
     // chunk j is issued at step j, its packed bytes are requested at step j + kLanes - 1 (so kLanes - 1 younger
@@ -815,6 +841,7 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
     }
     const int nchunks = (int)chunks.size();
     const uint64_t dstride = ((uint64_t)dst_cap + 15u) & ~15ull;
+    const bool stage_in = g_stage_pageable && !host_pinned(hrec), stage_out = g_stage_pageable && !host_pinned(hdst);
 
     auto issue = [&](int k) -> int {
         Lane& L = pp->lane[k % kLanes];
@@ -830,7 +857,13 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
         uint64_t* h_rel = L.h_meta.as<uint64_t>();
         uint32_t* h_len = reinterpret_cast<uint32_t*>(h_rel + cnt);
         for (uint32_t i = 0; i < cnt; i++) { h_rel[i] = rec_off[c.b0 + i] - c.lo; h_len[i] = raw_blocks ? raw_len[c.b0 + i] : 0u; }
-        CU(cudaMemcpyAsync(L.in.p, hrec + c.lo, span, cudaMemcpyHostToDevice, L.st));
+        const uint8_t* up = hrec + c.lo;
+        if (stage_in) {
+            CU(L.h_in.reserve(span));
+            plz4cu_internal_copy(L.h_in.p, up, span);
+            up = L.h_in.as<uint8_t>();
+        }
+        CU(cudaMemcpyAsync(L.in.p, up, span, cudaMemcpyHostToDevice, L.st));
         CU(cudaMemcpyAsync(L.off.p, h_rel, (uint64_t)cnt * 12, cudaMemcpyHostToDevice, L.st));
         DecodeArgs a{};
         a.rec_base = L.in.as<uint8_t>(); a.rec_off = L.off.as<uint64_t>();
@@ -841,7 +874,11 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
         CU(launch_decompress(a, L.st));
         g_launches++;
         CU(cudaMemcpyAsync(L.h_res.p, L.res.p, (uint64_t)cnt * 4, cudaMemcpyDeviceToHost, L.st));
-        if (dstride == dst_stride) {
+        if (stage_out) {
+            // down into the lane's pinned slab in one piece; finish() spreads the slots over the caller's buffer
+            CU(L.h_out.reserve((uint64_t)cnt * dstride));
+            CU(cudaMemcpyAsync(L.h_out.p, L.out.p, (uint64_t)cnt * dstride, cudaMemcpyDeviceToHost, L.st));
+        } else if (dstride == dst_stride) {
             CU(cudaMemcpyAsync(hdst + (uint64_t)c.b0 * dst_stride, L.out.p, (uint64_t)cnt * dstride, cudaMemcpyDeviceToHost, L.st));
         } else {
             CU(cudaMemcpy2DAsync(hdst + (uint64_t)c.b0 * dst_stride, dst_stride, L.out.p, dstride, dst_cap, cnt,
@@ -855,6 +892,11 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
         const Chunk& c = chunks[k];
         CU(cudaEventSynchronize(L.fin));
         memcpy(out_len + c.b0, L.h_res.p, (size_t)(c.b1 - c.b0) * 4);
+        if (stage_out) {
+            const uint32_t cnt = c.b1 - c.b0;
+            if (dstride == dst_stride) plz4cu_internal_copy(hdst + (uint64_t)c.b0 * dst_stride, L.h_out.p, (size_t)cnt * dstride);
+            else for (uint32_t i = 0; i < cnt; i++) memcpy(hdst + (uint64_t)(c.b0 + i) * dst_stride, L.h_out.as<uint8_t>() + (uint64_t)i * dstride, dst_cap);
+        }
         return 0;
     };
     int rc = 0;

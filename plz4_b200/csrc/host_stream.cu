@@ -435,6 +435,9 @@ std::vector<uint8_t> make_header(const plz4cu_opts_t& o)
 
 }  // namespace
 
+// the several-thread copy for the engine's own staging of pageable caller buffers (engine.cu)
+void plz4cu_internal_copy(void* dst, const void* src, size_t n) { bulk_copy_mt(dst, src, n, 1); }
+
 // ================================================================ Writer
 
 struct plz4cu_writer {
