@@ -707,6 +707,9 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
     const int nchunks = (int)chunks.size();
     uint64_t out_pos = 0;
     const bool stage_in = g_stage_pageable && !host_pinned(hsrc), stage_out = g_stage_pageable && !host_pinned(hout);
+    // a call of a block or two (the per-block shims): the caller waits for exactly this work, so the host spins on the stream
+    // instead of sleeping on an event (a blocking wait wakes up 50-100 us late, twice per call)
+    const bool tiny = nchunks == 1 && total_len <= (1u << 20);
 
     // stage 1: inputs up, kernels, packed offsets down
     auto issue = [&](int k) -> int {
@@ -753,7 +756,7 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
         Lane& L = pp->lane[k % kLanes];
         const Chunk& c = chunks[k];
         const uint32_t cnt = c.b1 - c.b0;
-        CU(cudaEventSynchronize(L.done));
+        if (tiny) CU(cudaStreamSynchronize(L.st)); else CU(cudaEventSynchronize(L.done));
         const uint64_t* hoff = L.h_res.as<uint64_t>();
         const uint64_t total = hoff[cnt];
         if (out_pos + total > packed_cap) return fail(PLZ4CU_ERR_ARG, "compress_batch_host: packed buffer too small");
@@ -769,8 +772,8 @@ int plz4cu_compress_batch_host(const void* src, const uint64_t* src_off, const u
     };
     auto finish = [&](int k) -> int {
         Lane& L = pp->lane[k % kLanes];
-        if (L.fin_recorded) CU(cudaEventSynchronize(L.fin));
-        else CU(cudaStreamSynchronize(L.st));             // error path: the chunk never got as far as post()
+        if (L.fin_recorded && !tiny) CU(cudaEventSynchronize(L.fin));
+        else CU(cudaStreamSynchronize(L.st));             // a tiny call, or the error path: the chunk never got as far as post()
         if (L.fin_recorded && L.out_bytes) { plz4cu_internal_copy(hout + L.out_pos, L.h_out.p, L.out_bytes); L.out_bytes = 0; }
         return 0;
     };
@@ -842,6 +845,7 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
     const int nchunks = (int)chunks.size();
     const uint64_t dstride = ((uint64_t)dst_cap + 15u) & ~15ull;
     const bool stage_in = g_stage_pageable && !host_pinned(hrec), stage_out = g_stage_pageable && !host_pinned(hdst);
+    const bool tiny = nchunks == 1 && total_out <= (1u << 20);      // (see compress_batch_host)
 
     auto issue = [&](int k) -> int {
         Lane& L = pp->lane[k % kLanes];
@@ -890,7 +894,7 @@ int plz4cu_decompress_batch_host(const void* recs, uint64_t recs_bytes, const ui
     auto finish = [&](int k) -> int {
         Lane& L = pp->lane[k % kLanes];
         const Chunk& c = chunks[k];
-        CU(cudaEventSynchronize(L.fin));
+        if (tiny) CU(cudaStreamSynchronize(L.st)); else CU(cudaEventSynchronize(L.fin));
         memcpy(out_len + c.b0, L.h_res.p, (size_t)(c.b1 - c.b0) * 4);
         if (stage_out) {
             const uint32_t cnt = c.b1 - c.b0;
