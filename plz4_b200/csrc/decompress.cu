@@ -1,5 +1,6 @@
-// decompress.cu — LZ4 block decode (sm_100a): one warp per block when a launch has many blocks, one CTA per block
-// ("team", second half of this file) when it has few, large ones.
+// decompress.cu — LZ4 block decode (sm_100a): one warp per block when a launch fills the SMs that way, two warps per
+// block ("duo": a parser and a copier) when it has fewer than 32 blocks per SM, one CTA per block ("team", second half
+// of this file) when it has few, large ones or only a handful.
 //
 // Replaces, for a whole batch of independent blocks, what plz4 does per block on a goroutine:
 //   blk/frame.go:79-81      size word > block size            -> PLZ4CU_E_OVERFLOW
@@ -235,11 +236,12 @@ __device__ __forceinline__ int32_t decode_block(const uint8_t* __restrict__ src,
     for (;;) {
         if (H.on && ip + 256 > H.done && H.done + 512 <= n) hash_along(H, src, min(ip + 1024, n), lane);
         // ---- 1. parse up to 32 shortcut sequences; lane k latches sequence k.
-        // The next 128 compressed bytes sit in registers (one word per lane).  Every lane first computes, for
-        // each of its own 4 bytes, how long a sequence header starting there would be (token + literals +
-        // offset [+ one length byte]); walking the token chain is then one shuffle per sequence instead of three
-        // dependent loads.  Headers that do not fit the simple shape (literal nibble 15, more than one length
-        // byte, too close to the end of the input) end the batch and go through decode_one.
+        // The next 128 compressed bytes are loaded one word per lane.  Every lane first computes, for each of its
+        // own 4 bytes, how long a sequence header starting there would be (token + literals + offset [+ one
+        // length byte]); lengths and window go to shared memory, and walking the token chain is then three
+        // instructions per sequence instead of three dependent global loads.  Headers that do not fit the simple
+        // shape (more than one length byte, a literal run above 63, too close to the end of the input) end the
+        // batch and go through decode_one.
         int nseq = 0;
         int my_lit = 0, my_litpos = 0, my_mlen = 0;
         // input position after my sequence: literals, offset, and the one extension byte a match nibble of 15 carries
